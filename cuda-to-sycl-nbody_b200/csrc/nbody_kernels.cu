@@ -1,0 +1,447 @@
+// nbody_kernels.cu -- hand-written sm_100a kernels of the all-pairs force + integrate step.
+//
+// What is computed is fixed by the reference kernel particle_interaction<BRANCH>
+// (src/simulator.cu:186-229) compiled with -use_fast_math; its sm_100a SASS does, per pair,
+//     r  = p_j + (-p_i)                      3 FADD.FTZ
+//     t  = ry*ry ; t = fma(rx,rx,t) ; t = fma(rz,rz,t)     FMUL + 2 FFMA
+//     d  = t + distEps                       FADD   (softening is added to r^2, :201)
+//     c  = d * (d*d)                         2 FMUL
+//     w  = MUFU.RSQ(c)
+//     a  = fma(r, w, a)                      3 FFMA, skipped when j == i
+// with one accumulator per component and j ascending.  FP32 addition is not associative and
+// the sums cancel heavily, so any other order differs from the reference by ~1e-5 relative at
+// N = 262144.  Every kernel here therefore keeps that exact op sequence and
+// order -- spelled in PTX with explicit .rn.ftz so ptxas cannot re-contract it -- and is
+// bit-identical to the reference; the speed comes from how the sequence is fed and issued:
+//
+//   * j-bodies are staged through shared memory in CTA-wide tiles (double buffered, one
+//     __syncthreads per tile) and read with warp-uniform (broadcast) LDS;
+//   * each thread register-blocks R i-bodies, so one LDS feeds R interactions;
+//   * the packed kernel pairs two i-bodies in the two lanes of Blackwell's f32x2 instructions
+//     (FADD2 / FMUL2 / FFMA2): 12 FP32 instructions serve TWO interactions, which takes the
+//     kernel off the issue-slot bound (13 slots/interaction) and onto the FMA-pipe bound;
+//     the j-body is a scalar operand broadcast to both lanes by the instruction itself
+//     (SASS operand form `R.F32`), so the tile stays in its HBM layout and costs one LDS.128;
+//   * no warp shuffles, no atomics, no j-split: the accumulate is a per-thread FMA chain.
+#include "nbody_kernels.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+namespace nbody {
+
+typedef unsigned long long u64;
+
+// ---- FP32 primitives with the reference's rounding/flush behaviour --------------------------
+__device__ __forceinline__ float fadd(float a, float b) {
+  float d;
+  asm("add.rn.ftz.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float fmul(float a, float b) {
+  float d;
+  asm("mul.rn.ftz.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float ffma(float a, float b, float c) {
+  float d;
+  asm("fma.rn.ftz.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float frsq(float a) {  // MUFU.RSQ, what rsqrt() is under -use_fast_math
+  float d;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(a));
+  return d;
+}
+// packed pairs: two independent IEEE lanes per instruction (sm_100+)
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// velocity / position update, src/simulator.cu:213-228 in the reference SASS op order
+__device__ __forceinline__ void integrate_component(float f, float &v, float &p, float dt, float G,
+                                                    float damping) {
+  float t = fmul(f, dt);
+  float vd = fmul(v, damping);
+  v = ffma(t, G, vd);
+  p = ffma(v, dt, p);
+}
+
+// =============================================================================================
+// packed kernel: R (even) i-bodies per thread, pairs (2p, 2p+1) share one f32x2 lane pair
+// =============================================================================================
+template <int R, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) force_packed_kernel(const StepArgs a) {
+  static_assert(R % 2 == 0, "packed kernel pairs i-bodies");
+  constexpr int NP = R / 2;
+  constexpr int TJ = BLOCK;  // one j-body per thread per tile fill
+  __shared__ __align__(16) float4 s_p[2][TJ];  // tile of j-bodies as they lie in HBM
+
+  const int tid = threadIdx.x;
+  const uint32_t tile_i = blockIdx.x * (uint32_t)(BLOCK * R);
+
+  u64 nx[NP], ny[NP], nz[NP];  // negated i positions, packed
+  u64 ax[NP], ay[NP], az[NP];  // accumulators, packed
+  float4 own[R];
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    uint32_t li = tile_i + k * BLOCK + tid;
+    uint32_t lc = li < a.i_count ? li : a.i_count - 1;
+    own[k] = a.pos[a.i_begin + lc];
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    nx[p] = pack2(-own[2 * p].x, -own[2 * p + 1].x);
+    ny[p] = pack2(-own[2 * p].y, -own[2 * p + 1].y);
+    nz[p] = pack2(-own[2 * p].z, -own[2 * p + 1].z);
+  }
+  if (a.flags & kFirstChunk) {
+#pragma unroll
+    for (int p = 0; p < NP; p++) ax[p] = ay[p] = az[p] = 0ull;
+  } else {
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      float4 c[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        uint32_t li = tile_i + (2 * p + h) * BLOCK + tid;
+        uint32_t lc = li < a.i_count ? li : a.i_count - 1;
+        c[h] = a.acc[lc];
+      }
+      ax[p] = pack2(c[0].x, c[1].x);
+      ay[p] = pack2(c[0].y, c[1].y);
+      az[p] = pack2(c[0].z, c[1].z);
+    }
+  }
+  const u64 eps2 = pack2(a.eps, a.eps);
+
+  const uint32_t nj = a.j_end - a.j_begin;
+  const uint32_t ntiles = (nj + TJ - 1) / TJ;
+
+  auto fill = [&](int buf, float4 v) { s_p[buf][tid] = v; };
+  auto fetch = [&](uint32_t t) -> float4 {
+    uint32_t j = a.j_begin + t * TJ + tid;
+    return a.pos[j < a.j_end ? j : a.j_end - 1];
+  };
+  auto interact = [&](int buf, int j) {
+    // one broadcast LDS.128 per j; pack2(q.x, q.x) costs nothing: ptxas encodes it as the
+    // scalar-broadcast operand form of FADD2 (`R.F32`), see profiles/sass_*.txt
+    const float4 q = s_p[buf][j];
+    const u64 qx = pack2(q.x, q.x), qy = pack2(q.y, q.y), qz = pack2(q.z, q.z);
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      u64 rx = fadd2(qx, nx[p]);
+      u64 ry = fadd2(qy, ny[p]);
+      u64 rz = fadd2(qz, nz[p]);
+      u64 t = fmul2(ry, ry);
+      t = ffma2(rx, rx, t);
+      t = ffma2(rz, rz, t);
+      u64 d = fadd2(t, eps2);
+      u64 c = fmul2(d, d);
+      c = fmul2(d, c);
+      float c0, c1;
+      unpack2(c, c0, c1);
+      u64 w = pack2(frsq(c0), frsq(c1));
+      ax[p] = ffma2(rx, w, ax[p]);
+      ay[p] = ffma2(ry, w, ay[p]);
+      az[p] = ffma2(rz, w, az[p]);
+    }
+  };
+
+  if (ntiles > 0) fill(0, fetch(0));
+  __syncthreads();
+  for (uint32_t t = 0; t < ntiles; t++) {
+    const int buf = t & 1;
+    float4 nxt;
+    const bool more = t + 1 < ntiles;
+    if (more) nxt = fetch(t + 1);
+    const uint32_t cnt = min((uint32_t)TJ, nj - t * TJ);
+    if (cnt == TJ) {
+#pragma unroll 8
+      for (int j = 0; j < TJ; j++) interact(buf, j);
+    } else {
+      for (uint32_t j = 0; j < cnt; j++) interact(buf, (int)j);
+    }
+    if (more) fill(buf ^ 1, nxt);
+    __syncthreads();
+  }
+
+  // epilogue: carry, dump, or integrate
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    const uint32_t li = tile_i + k * BLOCK + tid;
+    if (li >= a.i_count) continue;
+    float fx0, fx1, fy0, fy1, fz0, fz1;
+    unpack2(ax[k / 2], fx0, fx1);
+    unpack2(ay[k / 2], fy0, fy1);
+    unpack2(az[k / 2], fz0, fz1);
+    const float fx = (k & 1) ? fx1 : fx0, fy = (k & 1) ? fy1 : fy0, fz = (k & 1) ? fz1 : fz0;
+    if (!(a.flags & kLastChunk) || (a.flags & kAccelOut)) {
+      a.acc[li] = make_float4(fx, fy, fz, 0.0f);
+    } else {
+      float4 v = a.vel[li];
+      float4 p = own[k];
+      integrate_component(fx, v.x, p.x, a.dt, a.G, a.damping);
+      integrate_component(fy, v.y, p.y, a.dt, a.G, a.damping);
+      integrate_component(fz, v.z, p.z, a.dt, a.G, a.damping);
+      a.vel[li] = v;
+      a.pos_next[a.i_begin + li] = p;
+    }
+  }
+}
+
+// =============================================================================================
+// scalar kernel: R i-bodies per thread, scalar FADD/FMUL/FFMA; also the generic/faithful path
+// (BRANCH predicate for any eps, PREDICATED as shipped)
+// =============================================================================================
+template <int R, int BLOCK, int SELF>
+__global__ void __launch_bounds__(BLOCK) force_scalar_kernel(const StepArgs a) {
+  constexpr int TJ = BLOCK;
+  __shared__ __align__(16) float4 s_p[2][TJ];
+
+  const int tid = threadIdx.x;
+  const uint32_t tile_i = blockIdx.x * (uint32_t)(BLOCK * R);
+
+  float nx[R], ny[R], nz[R], ax[R], ay[R], az[R];
+  float4 own[R];
+  uint32_t gi[R];
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    uint32_t li = tile_i + k * BLOCK + tid;
+    uint32_t lc = li < a.i_count ? li : a.i_count - 1;
+    gi[k] = a.i_begin + lc;
+    own[k] = a.pos[gi[k]];
+    nx[k] = -own[k].x;
+    ny[k] = -own[k].y;
+    nz[k] = -own[k].z;
+    if (a.flags & kFirstChunk) {
+      ax[k] = ay[k] = az[k] = 0.0f;
+    } else {
+      float4 c = a.acc[lc];
+      ax[k] = c.x;
+      ay[k] = c.y;
+      az[k] = c.z;
+    }
+  }
+  const float eps = a.eps;
+  const uint32_t nj = a.j_end - a.j_begin;
+  const uint32_t ntiles = (nj + TJ - 1) / TJ;
+
+  auto fetch = [&](uint32_t t) -> float4 {
+    uint32_t j = a.j_begin + t * TJ + tid;
+    return a.pos[j < a.j_end ? j : a.j_end - 1];
+  };
+  auto interact = [&](int buf, int j, uint32_t gj) {
+    const float4 q = s_p[buf][j];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      float rx = fadd(q.x, nx[k]);
+      float ry = fadd(q.y, ny[k]);
+      float rz = fadd(q.z, nz[k]);
+      float t = fmul(ry, ry);
+      t = ffma(rx, rx, t);
+      t = ffma(rz, rz, t);
+      float d = fadd(t, eps);
+      float c = fmul(d, d);
+      c = fmul(d, c);
+      float w = frsq(c);
+      if (SELF == kSelfNone) {
+        ax[k] = ffma(rx, w, ax[k]);
+        ay[k] = ffma(ry, w, ay[k]);
+        az[k] = ffma(rz, w, az[k]);
+      } else if (SELF == kSelfBranch) {
+        if (gj != gi[k]) {
+          ax[k] = ffma(rx, w, ax[k]);
+          ay[k] = ffma(ry, w, ay[k]);
+          az[k] = ffma(rz, w, az[k]);
+        }
+      } else {  // as shipped: force += r * inv * (i == id)
+        const float sel = (gj == gi[k]) ? 1.0f : 0.0f;
+        ax[k] = ffma(fmul(rx, w), sel, ax[k]);
+        ay[k] = ffma(fmul(ry, w), sel, ay[k]);
+        az[k] = ffma(fmul(rz, w), sel, az[k]);
+      }
+    }
+  };
+
+  if (ntiles > 0) s_p[0][tid] = fetch(0);
+  __syncthreads();
+  for (uint32_t t = 0; t < ntiles; t++) {
+    const int buf = t & 1;
+    float4 nxt;
+    const bool more = t + 1 < ntiles;
+    if (more) nxt = fetch(t + 1);
+    const uint32_t cnt = min((uint32_t)TJ, nj - t * TJ);
+    const uint32_t gj0 = a.j_begin + t * TJ;
+    if (cnt == TJ) {
+#pragma unroll 8
+      for (int j = 0; j < TJ; j++) interact(buf, j, gj0 + j);
+    } else {
+      for (uint32_t j = 0; j < cnt; j++) interact(buf, (int)j, gj0 + j);
+    }
+    if (more) s_p[buf ^ 1][tid] = nxt;
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    const uint32_t li = tile_i + k * BLOCK + tid;
+    if (li >= a.i_count) continue;
+    if (!(a.flags & kLastChunk) || (a.flags & kAccelOut)) {
+      a.acc[li] = make_float4(ax[k], ay[k], az[k], 0.0f);
+    } else {
+      float4 v = a.vel[li];
+      float4 p = own[k];
+      integrate_component(ax[k], v.x, p.x, a.dt, a.G, a.damping);
+      integrate_component(ay[k], v.y, p.y, a.dt, a.G, a.damping);
+      integrate_component(az[k], v.z, p.z, a.dt, a.G, a.damping);
+      a.vel[li] = v;
+      a.pos_next[a.i_begin + li] = p;
+    }
+  }
+}
+
+// ---- layout helpers -------------------------------------------------------------------------
+__global__ void deinterleave_kernel(const float4 *__restrict__ src, float *__restrict__ x,
+                                    float *__restrict__ y, float *__restrict__ z, uint32_t count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float4 v = src[i];
+  x[i] = v.x;
+  y[i] = v.y;
+  z[i] = v.z;
+}
+__global__ void interleave_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                  const float *__restrict__ z, const float *__restrict__ m, float w,
+                                  float4 *__restrict__ dst, uint32_t count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  dst[i] = make_float4(x[i], y[i], z[i], m ? m[i] : w);
+}
+
+cudaError_t launch_deinterleave(const float4 *src, float *x, float *y, float *z, uint32_t count,
+                                cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  deinterleave_kernel<<<(count + 255) / 256, 256, 0, stream>>>(src, x, y, z, count);
+  return cudaGetLastError();
+}
+cudaError_t launch_interleave(const float *x, const float *y, const float *z, const float *m,
+                              float w, float4 *dst, uint32_t count, cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  interleave_kernel<<<(count + 255) / 256, 256, 0, stream>>>(x, y, z, m, w, dst, count);
+  return cudaGetLastError();
+}
+
+// ---- host side: configuration and dispatch ---------------------------------------------------
+
+// FP32 flush-to-zero product as the GPU evaluates c = d*(d*d) for r = 0, d = 0 + eps
+static float ftz(float v) { return (fpclassify(v) == FP_SUBNORMAL) ? copysignf(0.0f, v) : v; }
+
+bool eps_allows_unpredicated(float eps) {
+  volatile float d = ftz(0.0f + ftz(eps));
+  volatile float dd = ftz(d * d);
+  volatile float c = ftz(d * dd);
+  // rsqrt(c) must be finite and the self term fma(0, w, a) == a: c positive, normal, finite
+  return isfinite(c) && c > 0.0f && fpclassify(c) == FP_NORMAL;
+}
+
+KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uint32_t i_count,
+                           int sms) {
+  KernelConfig c;
+  const bool exact_unpred = eps_allows_unpredicated(eps);
+  if (calc_method != 0) {  // PREDICATED, as shipped
+    c = {0, 1, 128, kSelfPredicated};
+    return c;
+  }
+  if (requested_kernel == 1 /*GENERIC*/ || !exact_unpred) {
+    c = {0, 1, 128, kSelfBranch};
+    return c;
+  }
+  const int family = requested_kernel == 3 ? 2 : 1;
+  // i-bodies per CTA = block*r.  Keep at least ~4 CTA-tiles per SM so the tail of the grid is
+  // short; with fewer bodies fall back to narrower register blocking.
+  int r = 4, block = 128;
+  if ((uint64_t)i_count < (uint64_t)sms * 4u * 512u) r = 2;
+  if ((uint64_t)i_count < (uint64_t)sms * 4u * 256u) block = 64;
+  // tuning override for sweeps: NBODY_KERNEL_CONFIG="r,block" (only the exact unpredicated families)
+  if (const char *e = getenv("NBODY_KERNEL_CONFIG")) {
+    int er = 0, eb = 0;
+    if (sscanf(e, "%d,%d", &er, &eb) == 2 && er > 0 && eb > 0) {
+      r = er;
+      block = eb;
+    }
+  }
+  c = {family, r, block, kSelfNone};
+  return c;
+}
+
+const char *config_name(const KernelConfig &c, char *buf, size_t len) {
+  const char *fam = c.family == 1 ? "packed_f32x2" : (c.family == 2 ? "scalar_blocked" : "generic");
+  const char *self = c.self_mode == kSelfNone ? "nopred"
+                                              : (c.self_mode == kSelfBranch ? "branch" : "predicated");
+  snprintf(buf, len, "%s_r%d_b%d_%s", fam, c.r, c.block, self);
+  return buf;
+}
+
+template <int R, int BLOCK>
+static cudaError_t launch_packed(const StepArgs &a, cudaStream_t s) {
+  uint32_t grid = (a.i_count + BLOCK * R - 1) / (BLOCK * R);
+  force_packed_kernel<R, BLOCK><<<grid, BLOCK, 0, s>>>(a);
+  return cudaGetLastError();
+}
+template <int R, int BLOCK, int SELF>
+static cudaError_t launch_scalar(const StepArgs &a, cudaStream_t s) {
+  uint32_t grid = (a.i_count + BLOCK * R - 1) / (BLOCK * R);
+  force_scalar_kernel<R, BLOCK, SELF><<<grid, BLOCK, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_step(const KernelConfig &c, const StepArgs &a, cudaStream_t s) {
+  if (a.i_count == 0) return cudaSuccess;
+  if (c.family == 0) {
+    if (c.self_mode == kSelfPredicated) return launch_scalar<1, 128, kSelfPredicated>(a, s);
+    return launch_scalar<1, 128, kSelfBranch>(a, s);
+  }
+#define NB_PACKED(RR, BB) \
+  if (c.family == 1 && c.r == RR && c.block == BB) return launch_packed<RR, BB>(a, s);
+#define NB_SCALAR(RR, BB) \
+  if (c.family == 2 && c.r == RR && c.block == BB) return launch_scalar<RR, BB, kSelfNone>(a, s);
+  NB_PACKED(2, 64)
+  NB_PACKED(2, 128)
+  NB_PACKED(4, 64)
+  NB_PACKED(4, 128)
+  NB_PACKED(4, 256)
+  NB_PACKED(8, 64)
+  NB_PACKED(8, 128)
+  NB_SCALAR(2, 128)
+  NB_SCALAR(4, 64)
+  NB_SCALAR(4, 128)
+  NB_SCALAR(4, 256)
+  NB_SCALAR(8, 128)
+#undef NB_PACKED
+#undef NB_SCALAR
+  return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace nbody

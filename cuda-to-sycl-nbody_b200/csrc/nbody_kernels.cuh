@@ -1,0 +1,65 @@
+// nbody_kernels.cuh -- launch interface of the sm_100a force+integrate kernels.
+//
+// One launch = for every i-body of a shard, accumulate the softened-gravity force of the
+// j-bodies [j_begin, j_end) in ascending j with ONE FP32 accumulator per component
+// (reference loop: src/simulator.cu:196-211), optionally carrying the accumulators in/out
+// through `acc` so that a step can be cut into j-chunks without changing a single bit, and
+// optionally finishing with the reference's velocity/position update (src/simulator.cu:213-228).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nbody {
+
+enum StepFlags : int {
+  kFirstChunk = 1,  // accumulators start at +0 (else they are loaded from `acc`)
+  kLastChunk = 2,   // integrate and write vel / pos_next (else accumulators go to `acc`)
+  kAccelOut = 4,    // with kLastChunk: write raw force sums to `acc` instead of integrating
+};
+
+struct StepArgs {
+  const float4 *pos;  // n float4 (x,y,z,mass): j-bodies and the i-bodies' old positions
+  float4 *pos_next;   // n float4; [i_begin, i_begin+i_count) written when integrating
+  float4 *vel;        // i_count float4, shard-local index
+  float4 *acc;        // i_count float4, shard-local index (carried sums / accel output)
+  uint32_t n;
+  uint32_t i_begin, i_count;
+  uint32_t j_begin, j_end;
+  float eps, dt, G, damping;
+  int flags;
+};
+
+// self-term handling of the scalar kernels
+enum SelfMode : int {
+  kSelfNone = 0,        // no predicate: valid when rsqrt((0+eps)^3) is finite (self term adds +0)
+  kSelfBranch = 1,      // skip j == i             (src/simulator.cu:206)
+  kSelfPredicated = 2,  // multiply by (j == i)    (src/simulator.cu:209, as shipped)
+};
+
+struct KernelConfig {
+  int family;  // 0 = generic scalar (R=1, predicated), 1 = packed f32x2, 2 = scalar blocked
+  int r;       // i-bodies per thread
+  int block;   // threads per CTA
+  int self_mode;
+};
+
+// true when the unpredicated kernels reproduce the BRANCH result bit-for-bit for this eps:
+// c = eps*(eps*eps) evaluated in FP32 with flush-to-zero must be a positive normal number.
+bool eps_allows_unpredicated(float eps);
+
+// picks the configuration for a shard of i_count bodies on a device with `sms` SMs
+KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uint32_t i_count,
+                           int sms);
+const char *config_name(const KernelConfig &c, char *buf, size_t len);
+
+// asynchronous launch on `stream`; returns the CUDA error of the launch
+cudaError_t launch_step(const KernelConfig &c, const StepArgs &a, cudaStream_t stream);
+
+// float4 AoS -> three SoA arrays (read-back for the reference's ParticleData layout)
+cudaError_t launch_deinterleave(const float4 *src, float *x, float *y, float *z, uint32_t count,
+                                cudaStream_t stream);
+// three SoA arrays (+ optional mass, else w) -> float4 AoS
+cudaError_t launch_interleave(const float *x, const float *y, const float *z, const float *m,
+                              float w, float4 *dst, uint32_t count, cudaStream_t stream);
+
+}  // namespace nbody
