@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native all-pairs N-body step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--bodies N]
+
+Metric (BASELINE.json): G body-interactions/s = steps * N^2 / seconds / 1e9 (self pair
+included), and its fraction of the FP32 roofline at 20 flop/interaction.
+
+Workload: the reference's default-seeded disk galaxy with SimParam defaults (G=2, dt=0.005,
+damping=0.999998, distEps=1e-7, BRANCH), one force+integrate iteration per "step".
+  --gpus 1 : N = 1,048,576  (BASELINE configs[2]: 1xB200, 1M bodies)
+  --gpus>1 : N = 4,194,304  (BASELINE configs[3]: bodies sharded by i-range, NCCL position
+             exchange per step), strong scaling.  Launched by torchrun, one rank per GPU;
+             without torchrun env one process drives all N GPUs (the drop-in class's mode).
+
+Timing: W >= 3 untimed warm-up steps, then K steps, each timed ON THE DEVICE by CUDA events
+on the library's compute stream (nbody_last_step_device_ms: first launch -> last kernel and
+position exchange of that step), L2 flushed between steps, barrier + device synchronise on
+both sides of the timed region, MAX over ranks.  `value` has the state resident in HBM;
+`e2e` is the same step driven through the C ABI with HOST buffers (nbody_set_state from
+pinned memory + nbody_step + nbody_read_pos/vel into pinned memory) timed by the host clock.
+
+--impl reference: the reference's CPU implementation of this path cannot be built here (SYCL /
+OpenCL-CPU toolchain absent), so the arm times the oracle's C/OpenMP port of
+src_sycl/simulator.dp.cpp:315-360 on all host threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cuda-to-sycl-nbody_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+METRIC = "G body-interactions/s"
+FLOP_PER_INTERACTION = 20.0
+SMS, FP32_LANES = 148, 128
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def fp32_peak_tflops(peaks):
+    """FP32 FMA peak = SMs x 128 lanes x 2 flop x max SM clock (MEASURED_PEAKS.json: sm_max_mhz)."""
+    return SMS * FP32_LANES * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+
+
+# ---- torch.distributed plumbing (rendezvous, barrier, max over ranks) -------------------------
+class Dist:
+    """One process per GPU under torchrun; a no-op single rank otherwise."""
+
+    def __init__(self, backend: str | None = None):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.active = self.world > 1
+        self.backend = backend
+        if self.active:
+            import torch
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29577")
+            if backend is None:
+                backend = "nccl" if torch.cuda.is_available() else "gloo"
+            self.backend = backend
+            if backend == "nccl":
+                torch.cuda.set_device(self.local_rank)
+            dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
+            self.dist = dist
+            self.torch = torch
+
+    def _dev(self):
+        return self.torch.device("cuda", self.local_rank) if self.backend == "nccl" else self.torch.device("cpu")
+
+    def barrier(self):
+        if self.active:
+            self.dist.barrier()
+
+    def broadcast_bytes(self, payload: bytes | None, n: int) -> bytes:
+        """rank 0's `payload` (n bytes) to every rank"""
+        if not self.active:
+            return payload
+        t = self.torch.zeros(n, dtype=self.torch.uint8, device=self._dev())
+        if self.rank == 0:
+            t.copy_(self.torch.frombuffer(bytearray(payload), dtype=self.torch.uint8))
+        self.dist.broadcast(t, src=0)
+        return bytes(t.cpu().numpy().tobytes())
+
+    def max(self, v: float) -> float:
+        if not self.active:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self._dev())
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, v: float) -> float:
+        if not self.active:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self._dev())
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.active:
+            self.dist.destroy_process_group()
+
+
+# ---- clocks during the timed region -----------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                c = float(r[1])
+                if c < 500:  # idle sample before/after the load
+                    continue
+                sm.append(c)
+                mx.append(float(r[2]))
+                pw.append(float(r[3]))
+                for k, nm in enumerate(names):
+                    if r[4 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_median": statistics.median(pw) if pw else None, "samples_under_load": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---- CPU baseline (oracle port), bounded sample -----------------------------------------------
+def cpu_baseline(n_bodies: int, target_s: float = 12.0):
+    """Times the oracle's OpenMP port on forces of the first i_sample bodies against all N."""
+    import oracle_lib
+    if not os.path.exists(oracle_lib.ORACLE_LIB):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
+    o = oracle_lib.Oracle()
+    st = o.disk_galaxy(n_bodies)
+    probe = 256
+    t = o.time_accel(st[0], st[1], st[2], 1.0e-7, 0, probe, 1)
+    rate = probe * n_bodies / t
+    i_sample = int(min(n_bodies, max(probe, (rate * target_s / n_bodies) // 16 * 16)))
+    t = o.time_accel(st[0], st[1], st[2], 1.0e-7, 0, i_sample, 1)
+    g = i_sample * n_bodies / t / 1e9
+    return {"value": g, "unit": METRIC, "cores": o.num_threads(), "kind": "port",
+            "sample": f"forces of the first {i_sample} bodies against all {n_bodies} (1 pass, {t:.2f} s), "
+                      f"C/OpenMP restatement of src_sycl/simulator.dp.cpp:315-360, not the SYCL binary",
+            "seconds": t, "host_cpus": os.cpu_count()}
+
+
+def run_reference_arm(args, dist):
+    """--impl reference: the CPU port on all host threads, rank 0 only."""
+    if dist.rank != 0:
+        return
+    n = args.bodies or (1048576 if args.gpus == 1 else 4194304)
+    import oracle_lib
+    if not os.path.exists(oracle_lib.ORACLE_LIB):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
+    o = oracle_lib.Oracle()
+    st = o.disk_galaxy(n)
+    # bounded sample per step: ~3 s of CPU work
+    probe = 256
+    t = o.time_accel(st[0], st[1], st[2], 1.0e-7, 0, probe, 1)
+    i_sample = int(min(n, max(probe, (probe * n / t * 3.0 / n) // 16 * 16)))
+    for _ in range(args.warmup):
+        o.time_accel(st[0], st[1], st[2], 1.0e-7, 0, i_sample, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.time_accel(st[0], st[1], st[2], 1.0e-7, 0, i_sample, 1)
+    dt = time.perf_counter() - t0
+    g = args.steps * i_sample * n / dt / 1e9
+    sample = (f"each step = forces of {i_sample} of the {n} bodies against all {n} "
+              f"(C/OpenMP restatement of the reference's SYCL/OpenCL-CPU kernel; nbody_dpcpp itself cannot be built here)")
+    line = {"impl": "reference", "metric": METRIC, "value": g, "unit": "G inter/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"disk galaxy N={n}, SimParam defaults, bounded i-sample", "n_bodies": n},
+            "cpu_baseline": {"value": g, "unit": "G inter/s", "cores": o.num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": g, "unit": "G inter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200_arm(args, dist):
+    import numpy as np
+    import torch
+
+    import nbody_b200 as nb
+
+    nb.load_library()  # raises if the CUDA library is not built -- no fallback
+    if nb.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device visible; the product has no CPU path")
+    n = args.bodies or (1048576 if args.gpus == 1 else 4194304)
+    params = nb.SimParam(numParticles=n, simIterationsPerFrame=1)
+    multi_proc = dist.active
+    if multi_proc:
+        uid = dist.broadcast_bytes(nb.nccl_unique_id() if dist.rank == 0 else None, 128)
+        sim = nb.DiskGalaxySimulator(params, rank=dist.rank, world=dist.world, device=dist.local_rank, unique_id=uid)
+        torch.cuda.set_device(dist.local_rank)
+    else:
+        sim = nb.DiskGalaxySimulator(params, n_gpus=args.gpus)
+    dev = torch.device("cuda", dist.local_rank if multi_proc else 0)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def l2_flush():
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+
+    warmup = max(3, args.warmup)
+    for _ in range(warmup):
+        sim.stepSim()
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    sampler = ClockSampler(dist.local_rank if multi_proc else 0)
+    if dist.rank == 0:
+        sampler.start()
+    launches0 = sim.launchCount()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    wall0 = time.perf_counter()
+    dev_ms = 0.0
+    per_step = []
+    for _ in range(args.steps):
+        l2_flush()
+        sim.stepSim()
+        per_step.append(sim.getLastStepDeviceTime())
+        dev_ms += per_step[-1]
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    wall = time.perf_counter() - wall0
+    launches = sim.launchCount() - launches0
+    clocks = sampler.stop() if dist.rank == 0 else None
+    dev_ms = dist.max(dev_ms)
+    launches = int(dist.sum(launches))
+    value = args.steps * float(n) * n / (dev_ms * 1e-3) / 1e9
+
+    # ---- end to end through the C ABI with pinned host buffers -----------------------------------
+    host = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(6)]
+    hv = [t.numpy() for t in host]
+    sim.readInto(*hv)
+    e2e_steps = max(2, min(args.steps, 5))
+    sim.setState(*hv)
+    sim.stepSim()
+    sim.readInto(*hv)  # warm
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sim.setState(*hv)          # H2D: positions (all N) + velocities (owned shard)
+        sim.stepSim()              # one iteration
+        sim.readInto(*hv)          # D2H: positions + velocities, SoA, as recvFromDevice does
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    e2e_s = dist.max(time.perf_counter() - t0)
+    e2e_value = e2e_steps * float(n) * n / e2e_s / 1e9
+    ranks = dist.world if multi_proc else 1
+    if multi_proc:
+        h2d = sum(12 * n + 12 * nb.plan_shard(n, dist.world, r)[1] for r in range(dist.world))
+        d2h = 24 * n * dist.world
+    else:
+        h2d = 12 * n * args.gpus + 12 * n
+        d2h = 24 * n
+
+    kname = sim.kernelName()
+    sim.close()
+    if dist.rank != 0:
+        return
+
+    peaks, peak_src = measured_peaks()
+    peak_tf = fp32_peak_tflops(peaks)
+    n_gpus = args.gpus
+    achieved_tf = value * 1e9 * FLOP_PER_INTERACTION / 1e12 / n_gpus  # per GPU
+    # HBM side of the roofline, to show the kernel is not memory bound: algorithmic bytes per step
+    # per GPU = N*16 (positions read) + (N/P)*(16 vel r/w *2 + 16 pos write)
+    alg_bytes = n * 16 + (n / n_gpus) * 48
+    hbm_gbs = alg_bytes / (dev_ms / args.steps * 1e-3) / 1e9
+    roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None,
+                "peak_source": f"148 SMs x 128 FP32 lanes x 2 flop x sm_max_mhz of MEASURED_PEAKS.json ({peak_src})",
+                "convention": "20 flop/interaction (north_star); the exact 12-op recipe is FMA-pipe bound at 83.3% of this",
+                "per_gpu": True,
+                "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": peaks.get("hbm_gbs"), "frac": hbm_gbs / peaks.get("hbm_gbs", 6448.4),
+                        "algorithmic_bytes_per_step_per_gpu": alg_bytes},
+                "note": "path is FP32-FMA-pipe bound, neither HBM nor tensor: see DESIGN.md section 5"}
+    # dram traffic of the dominant kernel from the committed ncu capture, if present
+    tr = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            pass
+
+    line = {"metric": METRIC, "value": value, "unit": "G inter/s", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"reference disk galaxy (mt19937 seed 5489), N={n}, SimParam defaults, "
+                                   f"1 force+integrate iteration per step",
+                       "n_bodies": n, "kernel": kname, "sharding": f"i-range x{n_gpus}" if n_gpus > 1 else "none",
+                       "process_model": "torchrun, one rank per GPU" if multi_proc else "single process",
+                       "l2": "flushed between timed steps (256 MiB memset)",
+                       "baseline_config": "BASELINE.json configs[2]" if n_gpus == 1 else "BASELINE.json configs[3]"},
+            "pct_fp32_roofline": 100.0 * achieved_tf / peak_tf,
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": "G inter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                    "path": "nbody_set_state(pinned host SoA) + nbody_step + nbody_read_pos/vel(pinned host SoA)"},
+            "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
+            "ms_per_step_each": per_step}
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline(n)
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"error": str(e)}
+    if n_gpus == 1 and not args.no_ref_kernel:
+        try:
+            import refsim
+            if refsim.available():
+                r = refsim.RefSimulator(n, iters=1)
+                r.time_kernel(64, 1)
+                ms = r.time_kernel(64, 2) / 2
+                r.close()
+                line["reference_cuda_kernel"] = {"value": float(n) * n / ms / 1e6, "unit": "G inter/s", "ms_per_step": ms,
+                                                 "what": "unmodified particle_interaction<BRANCH> (oracle/_ref), gwSize 64, same GPU, same N"}
+        except Exception as e:  # noqa: BLE001
+            line["reference_cuda_kernel"] = {"error": str(e)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bodies", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-kernel", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        dist = Dist(backend="gloo")
+        try:
+            run_reference_arm(args, dist)
+        finally:
+            dist.close()
+        return
+    dist = Dist()
+    try:
+        run_b200_arm(args, dist)
+    finally:
+        dist.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -132,16 +132,17 @@ struct nbody_handle {
 
 namespace {
 
+// first body of rank r's shard: equal tile-aligned (128-body) shards, the last one ragged
+uint64_t shard_start(uint64_t n, int world, int r) {
+  uint64_t per = (n + world - 1) / world;
+  per = (per + 127u) / 128u * 128u;
+  uint64_t b = per * (uint64_t)r;
+  return b < n ? b : n;
+}
+
 void plan_shards(nbody_handle *h) {
-  const uint32_t n = h->n;
-  const int P = h->world;
-  uint32_t per = (n + P - 1) / P;
-  per = (per + 127u) / 128u * 128u;  // tile-aligned shards
-  h->shard_begin.resize(P + 1);
-  for (int r = 0; r <= P; r++) {
-    uint64_t b = (uint64_t)per * r;
-    h->shard_begin[r] = (uint32_t)(b < n ? b : n);
-  }
+  h->shard_begin.resize(h->world + 1);
+  for (int r = 0; r <= h->world; r++) h->shard_begin[r] = (uint32_t)shard_start(h->n, h->world, r);
 }
 
 void refresh_configs(nbody_handle *h) {
@@ -401,6 +402,13 @@ void nbody_default_params(nbody_params *out) {
   out->dist_eps = 1.0e-7f;
   out->gw_size = 64;
   out->calc_method = NBODY_CALC_BRANCH;
+}
+
+int nbody_plan_shard(uint64_t n, int world, int rank, uint64_t *begin, uint64_t *count) {
+  if (!begin || !count || world < 1 || rank < 0 || rank >= world) return fail(NBODY_E_INVALID, "bad shard query");
+  *begin = shard_start(n, world, rank);
+  *count = shard_start(n, world, rank + 1) - *begin;
+  return 0;
 }
 
 int nbody_nccl_unique_id(void *out128) {

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(BLOCK) force_packed_kernel(const StepArgs a) {
     if (more) nxt = fetch(t + 1);
     const uint32_t cnt = min((uint32_t)TJ, nj - t * TJ);
     if (cnt == TJ) {
-#pragma unroll 8
+#pragma unroll 32
       for (int j = 0; j < TJ; j++) interact(buf, j);
     } else {
       for (uint32_t j = 0; j < cnt; j++) interact(buf, (int)j);
@@ -191,6 +191,136 @@ __global__ void __launch_bounds__(BLOCK) force_packed_kernel(const StepArgs a) {
 #pragma unroll
   for (int k = 0; k < R; k++) {
     const uint32_t li = tile_i + k * BLOCK + tid;
+    if (li >= a.i_count) continue;
+    float fx0, fx1, fy0, fy1, fz0, fz1;
+    unpack2(ax[k / 2], fx0, fx1);
+    unpack2(ay[k / 2], fy0, fy1);
+    unpack2(az[k / 2], fz0, fz1);
+    const float fx = (k & 1) ? fx1 : fx0, fy = (k & 1) ? fy1 : fy0, fz = (k & 1) ? fz1 : fz0;
+    if (!(a.flags & kLastChunk) || (a.flags & kAccelOut)) {
+      a.acc[li] = make_float4(fx, fy, fz, 0.0f);
+    } else {
+      float4 v = a.vel[li];
+      float4 p = own[k];
+      integrate_component(fx, v.x, p.x, a.dt, a.G, a.damping);
+      integrate_component(fy, v.y, p.y, a.dt, a.G, a.damping);
+      integrate_component(fz, v.z, p.z, a.dt, a.G, a.damping);
+      a.vel[li] = v;
+      a.pos_next[a.i_begin + li] = p;
+    }
+  }
+}
+
+// =============================================================================================
+// warp-streaming packed kernel (the production kernel)
+//
+// Same arithmetic as force_packed_kernel, different feeding: every WARP stages its own 32-body
+// j-tiles (one coalesced LDG.128 per lane -> STS.128 -> __syncwarp -> 32 broadcast LDS.128),
+// double buffered, so there is no CTA-wide barrier and warps never wait for each other.  A CTA
+// is WARPS independent warps; with WARPS = 1 the hardware block scheduler balances the grid at
+// warp granularity.  The host caps the number of resident CTAs per SM through the dynamic
+// shared-memory size so that the grid runs as an integer number of equally full "generations"
+// (see plan_wstream): all SM sub-partitions then keep >= 5-7 warps until the very end, which
+// is what the FMA pipe needs to stay saturated (tools/ubench_fma2.cu, profiles/).
+// =============================================================================================
+template <int R, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) force_wstream_kernel(const StepArgs a) {
+  static_assert(R % 2 == 0, "packed kernel pairs i-bodies");
+  constexpr int NP = R / 2;
+  constexpr int TJ = 32;
+  __shared__ __align__(16) float4 s_tile[WARPS][2][TJ];
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t warp_i = (blockIdx.x * (uint32_t)WARPS + warp) * (uint32_t)(32 * R);
+  if (warp_i >= a.i_count) return;  // no CTA-wide synchronisation anywhere below
+  float4(*tile)[TJ] = s_tile[warp];
+
+  u64 nx[NP], ny[NP], nz[NP];
+  u64 ax[NP], ay[NP], az[NP];
+  float4 own[R];
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    uint32_t li = warp_i + k * 32 + lane;
+    uint32_t lc = li < a.i_count ? li : a.i_count - 1;
+    own[k] = a.pos[a.i_begin + lc];
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    nx[p] = pack2(-own[2 * p].x, -own[2 * p + 1].x);
+    ny[p] = pack2(-own[2 * p].y, -own[2 * p + 1].y);
+    nz[p] = pack2(-own[2 * p].z, -own[2 * p + 1].z);
+  }
+  if (a.flags & kFirstChunk) {
+#pragma unroll
+    for (int p = 0; p < NP; p++) ax[p] = ay[p] = az[p] = 0ull;
+  } else {
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      float4 c[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        uint32_t li = warp_i + (2 * p + h) * 32 + lane;
+        uint32_t lc = li < a.i_count ? li : a.i_count - 1;
+        c[h] = a.acc[lc];
+      }
+      ax[p] = pack2(c[0].x, c[1].x);
+      ay[p] = pack2(c[0].y, c[1].y);
+      az[p] = pack2(c[0].z, c[1].z);
+    }
+  }
+  const u64 eps2 = pack2(a.eps, a.eps);
+  const uint32_t nj = a.j_end - a.j_begin;
+  const uint32_t ntiles = (nj + TJ - 1) / TJ;
+
+  auto fetch = [&](uint32_t t) -> float4 {
+    uint32_t j = a.j_begin + t * TJ + lane;
+    return a.pos[j < a.j_end ? j : a.j_end - 1];
+  };
+  auto interact = [&](int buf, int j) {
+    const float4 q = tile[buf][j];
+    const u64 qx = pack2(q.x, q.x), qy = pack2(q.y, q.y), qz = pack2(q.z, q.z);
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      u64 rx = fadd2(qx, nx[p]);
+      u64 ry = fadd2(qy, ny[p]);
+      u64 rz = fadd2(qz, nz[p]);
+      u64 t = fmul2(ry, ry);
+      t = ffma2(rx, rx, t);
+      t = ffma2(rz, rz, t);
+      u64 d = fadd2(t, eps2);
+      u64 c = fmul2(d, d);
+      c = fmul2(d, c);
+      float c0, c1;
+      unpack2(c, c0, c1);
+      u64 w = pack2(frsq(c0), frsq(c1));
+      ax[p] = ffma2(rx, w, ax[p]);
+      ay[p] = ffma2(ry, w, ay[p]);
+      az[p] = ffma2(rz, w, az[p]);
+    }
+  };
+
+  if (ntiles > 0) tile[0][lane] = fetch(0);
+  __syncwarp();
+  for (uint32_t t = 0; t < ntiles; t++) {
+    const int buf = t & 1;
+    float4 nxt;
+    const bool more = t + 1 < ntiles;
+    if (more) nxt = fetch(t + 1);
+    const uint32_t cnt = min((uint32_t)TJ, nj - t * TJ);
+    if (cnt == TJ) {
+#pragma unroll
+      for (int j = 0; j < TJ; j++) interact(buf, j);
+    } else {
+      for (uint32_t j = 0; j < cnt; j++) interact(buf, (int)j);
+    }
+    if (more) tile[buf ^ 1][lane] = nxt;
+    __syncwarp();
+  }
+
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    const uint32_t li = warp_i + k * 32 + lane;
     if (li >= a.i_count) continue;
     float fx0, fx1, fy0, fy1, fz0, fz1;
     unpack2(ax[k / 2], fx0, fx1);
@@ -371,33 +501,43 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
   KernelConfig c;
   const bool exact_unpred = eps_allows_unpredicated(eps);
   if (calc_method != 0) {  // PREDICATED, as shipped
-    c = {0, 1, 128, kSelfPredicated};
+    c = {0, 1, 128, kSelfPredicated, sms};
     return c;
   }
   if (requested_kernel == 1 /*GENERIC*/ || !exact_unpred) {
-    c = {0, 1, 128, kSelfBranch};
+    c = {0, 1, 128, kSelfBranch, sms};
     return c;
   }
-  const int family = requested_kernel == 3 ? 2 : 1;
-  // i-bodies per CTA = block*r.  Keep at least ~4 CTA-tiles per SM so the tail of the grid is
-  // short; with fewer bodies fall back to narrower register blocking.
+  // family: 3 = warp-streaming packed (AUTO), 1 = CTA-tiled packed, 2 = CTA-tiled scalar
+  int family = requested_kernel == 3 ? 2 : (requested_kernel == 2 ? 1 : 3);
   int r = 4, block = 128;
-  if ((uint64_t)i_count < (uint64_t)sms * 4u * 512u) r = 2;
-  if ((uint64_t)i_count < (uint64_t)sms * 4u * 256u) block = 64;
-  // tuning override for sweeps: NBODY_KERNEL_CONFIG="r,block" (only the exact unpredicated families)
+  if (family == 3) {
+    // one warp per CTA; R = 4 i-bodies per lane unless that leaves fewer than ~5 warps per SM
+    // sub-partition, then R = 2 doubles the number of warps
+    block = 32;
+    if ((uint64_t)i_count < (uint64_t)sms * 20u * 128u) r = 2;
+  } else {
+    // i-bodies per CTA = block*r.  Keep at least ~4 CTA-tiles per SM so the tail of the grid is
+    // short; with fewer bodies fall back to narrower register blocking.
+    if ((uint64_t)i_count < (uint64_t)sms * 4u * 512u) r = 2;
+    if ((uint64_t)i_count < (uint64_t)sms * 4u * 256u) block = 64;
+  }
+  // tuning override for sweeps: NBODY_KERNEL_CONFIG="r,block[,family]" (exact unpredicated families)
   if (const char *e = getenv("NBODY_KERNEL_CONFIG")) {
-    int er = 0, eb = 0;
-    if (sscanf(e, "%d,%d", &er, &eb) == 2 && er > 0 && eb > 0) {
+    int er = 0, eb = 0, ef = 0;
+    int got = sscanf(e, "%d,%d,%d", &er, &eb, &ef);
+    if (got >= 2 && er > 0 && eb > 0) {
       r = er;
       block = eb;
+      if (got == 3 && ef >= 1 && ef <= 3) family = ef;
     }
   }
-  c = {family, r, block, kSelfNone};
+  c = {family, r, block, kSelfNone, sms};
   return c;
 }
 
 const char *config_name(const KernelConfig &c, char *buf, size_t len) {
-  const char *fam = c.family == 1 ? "packed_f32x2" : (c.family == 2 ? "scalar_blocked" : "generic");
+  const char *fam = c.family == 1 ? "packed_f32x2" : (c.family == 2 ? "scalar_blocked" : (c.family == 3 ? "wstream_f32x2" : "generic"));
   const char *self = c.self_mode == kSelfNone ? "nopred"
                                               : (c.self_mode == kSelfBranch ? "branch" : "predicated");
   snprintf(buf, len, "%s_r%d_b%d_%s", fam, c.r, c.block, self);
@@ -417,12 +557,93 @@ static cudaError_t launch_scalar(const StepArgs &a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// ---- warp-streaming kernel: residency planning ------------------------------------------------
+// The grid is `ctas` identical CTAs.  If an SM can hold k_max of them, the grid runs in
+// gens = ceil(ctas_per_sm / k_max) generations; capping residency at k = ceil(ctas_per_sm / gens)
+// makes every generation equally full instead of leaving a thin last one (e.g. 55.4 CTAs/SM
+// -> 28 + 27.4 rather than 32 + 23.4).  The cap is enforced with dynamic shared memory.
+struct WstreamPlan {
+  int k_cap;          // resident CTAs per SM to aim for
+  size_t dyn_smem;    // dynamic shared memory per CTA that enforces it
+};
+
+template <int R, int WARPS>
+static cudaError_t plan_wstream(uint32_t ctas, int sms, WstreamPlan *plan) {
+  auto kern = force_wstream_kernel<R, WARPS>;
+  static bool attr_done = false;  // per instantiation
+  cudaError_t e;
+  if (!attr_done) {
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
+    attr_done = true;
+  }
+  int k_max = 0;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k_max, kern, 32 * WARPS, 0)) != cudaSuccess) return e;
+  if (k_max < 1) return cudaErrorInvalidConfiguration;
+  const double per_sm = (double)ctas / sms;
+  int gens = (int)ceil(per_sm / k_max);
+  if (gens < 1) gens = 1;
+  int k = (int)ceil(per_sm / gens);
+  if (k > k_max) k = k_max;
+  if (k < 1) k = 1;
+  if (const char *env = getenv("NBODY_RESIDENT_CTAS")) {  // tuning override
+    int v = atoi(env);
+    if (v >= 1 && v <= k_max) k = v;
+  }
+  size_t dyn = 0;
+  if (k < k_max) {
+    // largest dynamic size that still lets k CTAs fit, found with the occupancy API itself
+    size_t lo = 0, hi = 200 * 1024;
+    while (hi - lo > 256) {
+      size_t mid = (lo + hi) / 2;
+      int occ = 0;
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * WARPS, mid)) != cudaSuccess) return e;
+      if (occ >= k) lo = mid; else hi = mid;
+    }
+    dyn = lo;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * WARPS, dyn);
+    if (occ != k) dyn = 0;  // cannot hit k exactly: leave the hardware limit
+  }
+  plan->k_cap = k;
+  plan->dyn_smem = dyn;
+  return cudaSuccess;
+}
+
+template <int R, int WARPS>
+static cudaError_t launch_wstream(const StepArgs &a, int sms, cudaStream_t s) {
+  const uint32_t warps = (a.i_count + 32 * R - 1) / (32 * R);
+  const uint32_t ctas = (warps + WARPS - 1) / WARPS;
+  // the plan depends only on (ctas, sms): cache the last one per instantiation
+  static uint32_t cached_ctas = 0;
+  static int cached_sms = 0;
+  static WstreamPlan cached{};
+  if (cached_ctas != ctas || cached_sms != sms) {
+    cudaError_t e = plan_wstream<R, WARPS>(ctas, sms, &cached);
+    if (e != cudaSuccess) return e;
+    cached_ctas = ctas;
+    cached_sms = sms;
+  }
+  force_wstream_kernel<R, WARPS><<<ctas, 32 * WARPS, cached.dyn_smem, s>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_step(const KernelConfig &c, const StepArgs &a, cudaStream_t s) {
   if (a.i_count == 0) return cudaSuccess;
   if (c.family == 0) {
     if (c.self_mode == kSelfPredicated) return launch_scalar<1, 128, kSelfPredicated>(a, s);
     return launch_scalar<1, 128, kSelfBranch>(a, s);
   }
+#define NB_WSTREAM(RR, WW) \
+  if (c.family == 3 && c.r == RR && c.block == 32 * WW) return launch_wstream<RR, WW>(a, c.sms, s);
+  NB_WSTREAM(2, 1)
+  NB_WSTREAM(4, 1)
+  NB_WSTREAM(6, 1)
+  NB_WSTREAM(8, 1)
+  NB_WSTREAM(2, 2)
+  NB_WSTREAM(4, 2)
+  NB_WSTREAM(4, 4)
+#undef NB_WSTREAM
 #define NB_PACKED(RR, BB) \
   if (c.family == 1 && c.r == RR && c.block == BB) return launch_packed<RR, BB>(a, s);
 #define NB_SCALAR(RR, BB) \
@@ -434,6 +655,7 @@ cudaError_t launch_step(const KernelConfig &c, const StepArgs &a, cudaStream_t s
   NB_PACKED(4, 256)
   NB_PACKED(8, 64)
   NB_PACKED(8, 128)
+  NB_SCALAR(2, 64)
   NB_SCALAR(2, 128)
   NB_SCALAR(4, 64)
   NB_SCALAR(4, 128)

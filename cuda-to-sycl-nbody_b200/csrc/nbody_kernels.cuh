@@ -37,10 +37,12 @@ enum SelfMode : int {
 };
 
 struct KernelConfig {
-  int family;  // 0 = generic scalar (R=1, predicated), 1 = packed f32x2, 2 = scalar blocked
+  int family;  // 0 = generic scalar (R=1, predicated), 1 = CTA-tiled packed f32x2,
+               // 2 = CTA-tiled scalar blocked, 3 = warp-streaming packed f32x2 (production)
   int r;       // i-bodies per thread
   int block;   // threads per CTA
   int self_mode;
+  int sms;     // SM count of the device the launch goes to (residency planning)
 };
 
 // true when the unpredicated kernels reproduce the BRANCH result bit-for-bit for this eps:

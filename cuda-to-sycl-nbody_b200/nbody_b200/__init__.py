@@ -27,7 +27,7 @@ KERNEL_AUTO, KERNEL_GENERIC, KERNEL_PACKED, KERNEL_SCALAR = 0, 1, 2, 3
 # every symbol include/nbody_b200.h declares (checked by tests/test_capi_cpu.py)
 ABI_SYMBOLS = [
     "nbody_abi_version", "nbody_last_error", "nbody_device_count", "nbody_default_params",
-    "nbody_generate_disk_galaxy", "nbody_create", "nbody_create_rank", "nbody_nccl_unique_id",
+    "nbody_generate_disk_galaxy", "nbody_plan_shard", "nbody_create", "nbody_create_rank", "nbody_nccl_unique_id",
     "nbody_destroy", "nbody_set_kernel", "nbody_kernel_name", "nbody_set_state", "nbody_set_mass",
     "nbody_step", "nbody_last_step_ms", "nbody_last_step_device_ms", "nbody_launch_count",
     "nbody_read_pos", "nbody_read_vel", "nbody_read_pos_f4", "nbody_read_vel_f4",
@@ -93,6 +93,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.nbody_default_params.argtypes = [ctypes.POINTER(Params)]
     lib.nbody_default_params.restype = None
     lib.nbody_generate_disk_galaxy.argtypes = [ctypes.c_uint64] + [_fp] * 6
+    lib.nbody_plan_shard.argtypes = [ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
     lib.nbody_create.argtypes = [ctypes.POINTER(Params), ctypes.c_int, ctypes.POINTER(H)]
     lib.nbody_create_rank.argtypes = [ctypes.POINTER(Params), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_void_p, ctypes.POINTER(H)]
@@ -149,6 +151,14 @@ def generate_disk_galaxy(n: int):
     arrs = [np.empty(n, np.float32) for _ in range(6)]
     _check(lib, lib.nbody_generate_disk_galaxy(n, *[_ptr(a) for a in arrs]), "nbody_generate_disk_galaxy")
     return arrs
+
+
+def plan_shard(n: int, world: int, rank: int) -> tuple[int, int]:
+    """(begin, count) of the i-range rank `rank` of `world` owns."""
+    lib = load_library()
+    b, c = ctypes.c_uint64(), ctypes.c_uint64()
+    _check(lib, lib.nbody_plan_shard(n, world, rank, ctypes.byref(b), ctypes.byref(c)), "nbody_plan_shard")
+    return int(b.value), int(c.value)
 
 
 def nccl_unique_id() -> bytes:

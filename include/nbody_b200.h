@@ -80,6 +80,13 @@ void        nbody_default_params(nbody_params *out);
 int nbody_generate_disk_galaxy(uint64_t n, float *x, float *y, float *z,
                                float *vx, float *vy, float *vz);
 
+/*
+ * Host-only: the contiguous i-range [*begin, *begin + *count) that rank `rank` of `world` owns
+ * for n bodies (shards are multiples of 128 bodies except the last).  New functionality: the
+ * reference is single-GPU (device 0 hard-wired, src/simulator.cu:40).
+ */
+int nbody_plan_shard(uint64_t n, int world, int rank, uint64_t *begin, uint64_t *count);
+
 /* ---- simulator object ---------------------------------------------------------------- */
 
 /*

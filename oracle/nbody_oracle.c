@@ -113,9 +113,22 @@ int oracle_disk_galaxy(uint64_t n, float *x, float *y, float *z, float *vx, floa
 
 /* ------------------------------------------------------------------------------------------ */
 
-static void set_ftz(void) {
+/* FTZ | DAZ while the restated kernel runs (the reference kernel is all .ftz); the caller's
+ * floating-point environment is restored afterwards (the master thread is the Python thread) */
+static unsigned set_ftz(void) {
 #if defined(__x86_64__)
-  _mm_setcsr(_mm_getcsr() | 0x8040u); /* FTZ | DAZ: the reference kernel is all .ftz */
+  unsigned old = _mm_getcsr();
+  _mm_setcsr(old | 0x8040u);
+  return old;
+#else
+  return 0;
+#endif
+}
+static void restore_csr(unsigned old) {
+#if defined(__x86_64__)
+  _mm_setcsr(old);
+#else
+  (void)old;
 #endif
 }
 
@@ -187,7 +200,7 @@ int oracle_accel(uint64_t n, const float *x, const float *y, const float *z, flo
   int64_t nblk = (int64_t)((i_end - i_begin + LANES - 1) / LANES);
 #pragma omp parallel
   {
-    set_ftz();
+    unsigned csr = set_ftz();
 #pragma omp for schedule(dynamic, 4)
     for (int64_t b = 0; b < nblk; b++) {
       uint64_t i0 = i_begin + (uint64_t)b * LANES;
@@ -199,6 +212,7 @@ int oracle_accel(uint64_t n, const float *x, const float *y, const float *z, flo
         accel_block_pred(n, x, y, z, eps, i0, cnt, ax + (i0 - i_begin), ay + (i0 - i_begin),
                          az + (i0 - i_begin));
     }
+    restore_csr(csr);
   }
   return 0;
 }
@@ -240,12 +254,13 @@ int oracle_step(uint64_t n, float *x, float *y, float *z, float *vx, float *vy, 
   for (int it = 0; it < iters; it++) {
     int rc = oracle_accel(n, x, y, z, eps, method, 0, n, ax, ay, az);
     if (rc) { free(ax); return rc; }
-    set_ftz();
+    unsigned csr = set_ftz();
     for (uint64_t i = 0; i < n; i++) {
       integrate1(ax[i], &vx[i], &x[i], dt, G, damping);
       integrate1(ay[i], &vy[i], &y[i], dt, G, damping);
       integrate1(az[i], &vz[i], &z[i], dt, G, damping);
     }
+    restore_csr(csr);
   }
   free(ax);
   return 0;
@@ -279,19 +294,23 @@ int oracle_num_threads(void) {
 #endif
 }
 
-/* FNV-1a-64 over the bit patterns of (x,y,z,vx,vy,vz) per body in index order */
-uint64_t oracle_fnv1a64_state(uint64_t n, const float *x, const float *y, const float *z,
-                              const float *vx, const float *vy, const float *vz) {
+/* FNV-1a-64 over the float bit patterns of k arrays, interleaved per body (a0[i], a1[i], ...) */
+uint64_t oracle_fnv1a64(uint64_t n, int k, const float *const *arr) {
   uint64_t h = 1469598103934665603ull;
-  const float *arr[6] = {x, y, z, vx, vy, vz};
   for (uint64_t i = 0; i < n; i++)
-    for (int k = 0; k < 6; k++) {
+    for (int a = 0; a < k; a++) {
       uint32_t b;
-      memcpy(&b, &arr[k][i], 4);
+      memcpy(&b, &arr[a][i], 4);
       for (int s = 0; s < 4; s++) {
         h ^= (b >> (8 * s)) & 0xffu;
         h *= 1099511628211ull;
       }
     }
   return h;
+}
+
+uint64_t oracle_fnv1a64_state(uint64_t n, const float *x, const float *y, const float *z,
+                              const float *vx, const float *vy, const float *vz) {
+  const float *arr[6] = {x, y, z, vx, vy, vz};
+  return oracle_fnv1a64(n, 6, arr);
 }

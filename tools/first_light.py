@@ -56,6 +56,7 @@ def time_variant(n, kernel, cfg, iters, reps=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--sizes", default="")
     args = ap.parse_args()
     out = {"parity": [], "sweep": [], "reference_kernel": []}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -100,7 +101,7 @@ def main():
         out["parity"].append(rec)
 
     # ---- 3. reference kernel throughput (the kernel to beat) ----
-    for n in ([262144] if args.quick else [262144, 1048576]):
+    for n in ([] if args.quick else [1048576]):
         ref = refsim.RefSimulator(n, iters=1)
         for gw in (64, 128, 256):
             ref.time_kernel(gw, 1)
@@ -111,10 +112,13 @@ def main():
         ref.close()
 
     # ---- 4. variant sweep ----
-    sizes = [262144] if args.quick else [262144, 1048576]
-    variants = [(nb.KERNEL_PACKED, c) for c in ("2,64", "2,128", "4,64", "4,128", "4,256", "8,64", "8,128")]
-    variants += [(nb.KERNEL_SCALAR, c) for c in ("2,128", "4,64", "4,128", "4,256", "8,128")]
-    variants += [(nb.KERNEL_GENERIC, "")]
+    sizes = [262144] if args.quick else [262144, 524288, 1048576]
+    if args.sizes:
+        sizes = [int(v) for v in args.sizes.split(",")]
+    variants = [(nb.KERNEL_AUTO, "")]
+    variants += [(nb.KERNEL_AUTO, c) for c in ("2,32,3", "4,32,3", "6,32,3", "8,32,3", "2,64,3", "4,64,3", "4,128,3")]
+    variants += [(nb.KERNEL_PACKED, c) for c in ("2,128,1", "4,256,1")]
+    variants += [(nb.KERNEL_SCALAR, c) for c in ("4,256,2",)]
     for n in sizes:
         for kernel, cfg in variants:
             iters = 4 if n <= 262144 else 1
