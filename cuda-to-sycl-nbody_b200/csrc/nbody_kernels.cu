@@ -570,12 +570,16 @@ struct WstreamPlan {
 template <int R, int WARPS>
 static cudaError_t plan_wstream(uint32_t ctas, int sms, WstreamPlan *plan) {
   auto kern = force_wstream_kernel<R, WARPS>;
-  static bool attr_done = false;  // per instantiation
+  // function attributes are per device: a single process may drive several GPUs
+  static bool attr_done[64] = {false};
   cudaError_t e;
-  if (!attr_done) {
+  int dev = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!attr_done[dev]) {
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
-    attr_done = true;
+    attr_done[dev] = true;
   }
   int k_max = 0;
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k_max, kern, 32 * WARPS, 0)) != cudaSuccess) return e;
@@ -614,17 +618,20 @@ template <int R, int WARPS>
 static cudaError_t launch_wstream(const StepArgs &a, int sms, cudaStream_t s) {
   const uint32_t warps = (a.i_count + 32 * R - 1) / (32 * R);
   const uint32_t ctas = (warps + WARPS - 1) / WARPS;
-  // the plan depends only on (ctas, sms): cache the last one per instantiation
-  static uint32_t cached_ctas = 0;
-  static int cached_sms = 0;
-  static WstreamPlan cached{};
-  if (cached_ctas != ctas || cached_sms != sms) {
-    cudaError_t e = plan_wstream<R, WARPS>(ctas, sms, &cached);
-    if (e != cudaSuccess) return e;
-    cached_ctas = ctas;
-    cached_sms = sms;
+  // the plan depends on (device, ctas): cache the last one per device and instantiation
+  struct Cached { uint32_t ctas = 0; int sms = 0; WstreamPlan plan{}; };
+  static Cached cache[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  Cached &c = cache[dev];
+  if (c.ctas != ctas || c.sms != sms) {
+    if ((e = plan_wstream<R, WARPS>(ctas, sms, &c.plan)) != cudaSuccess) return e;
+    c.ctas = ctas;
+    c.sms = sms;
   }
-  force_wstream_kernel<R, WARPS><<<ctas, 32 * WARPS, cached.dyn_smem, s>>>(a);
+  force_wstream_kernel<R, WARPS><<<ctas, 32 * WARPS, c.plan.dyn_smem, s>>>(a);
   return cudaGetLastError();
 }
 
