@@ -322,3 +322,29 @@ def test_step_timing_and_launch_count(nb):
     assert sim.getLastStepTime() > 0 and sim.getLastStepDeviceTime() > 0
     assert "B200" in sim.getDeviceName() or len(sim.getDeviceName()) > 0
     sim.close()
+
+
+def test_cxx_dropin_binaries(nb):
+    """The reference's own main (src/nbody.cpp, compiled against OUR simulator.cuh) and our
+    headless driver: same argv contract (src/sim_param.cpp:40-67) and the same stdout line
+    (src/nbody.cpp:120-122), printed after the two warm-up frames."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = re.compile(r"^At step (\d+) kernel time is \S+ and mean is \S+ and stddev is: \S+$")
+    ran = 0
+    for exe in ("nbody_b200", "nbody_refmain"):
+        path = os.path.join(root, "cuda-to-sycl-nbody_b200", "bin", exe)
+        if not os.path.exists(path):
+            continue
+        r = subprocess.run([path, "8", "3", "0.999", "0.001", "1.0e-3", "2.0", "6", "128", "BRANCH"],
+                           capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        rows = [l for l in r.stdout.splitlines() if l.strip()]
+        assert [int(line.match(l).group(1)) for l in rows] == [3, 4, 5, 6], rows
+        ran += 1
+    assert ran >= 1, "no drop-in binary built"
+    bad = subprocess.run([os.path.join(root, "cuda-to-sycl-nbody_b200", "bin", "nbody_b200"), "8", "1", "1", "1", "1",
+                          "1", "1", "64", "NOPE"], capture_output=True, text=True)
+    assert bad.returncode != 0  # std::invalid_argument, as the reference (src/sim_param.cpp:36)

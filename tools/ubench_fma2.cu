@@ -112,7 +112,7 @@ __global__ void k_body(float *out, int iters, float qx, float qy, float qz, floa
 // same body, j-body read from a 32-entry shared-memory tile with a warp-uniform (broadcast) address
 // SRC: 0 = LDS.128 broadcast, 1 = per-lane register tile + 3 SHFL, 2 = LDS.128 + tile refilled from
 // global every 32 j (the production warp-streaming loop)
-template <int NP, int SRC, bool WITH_MUFU = true, int PF = 0, int U = 8>
+template <int NP, int SRC, bool WITH_MUFU = true, int PF = 0, int U = 8, int VAR = 0>
 __global__ void k_body_mem(float *out, const float4 *gpos, int iters, float eps, long long *cyc) {
   __shared__ __align__(16) float4 tile[16][2][32];
   __shared__ __align__(16) ulonglong2 dxy[16][32];
@@ -164,7 +164,10 @@ __global__ void k_body_mem(float *out, const float4 *gpos, int iters, float eps,
         u64 c = fmul2(d, d); c = fmul2(d, c);
         float c0, c1; unpack2(c, c0, c1);
         u64 w = WITH_MUFU ? pack2(frsq(c0), frsq(c1)) : c;
-        ax[p] = ffma2(rx, w, ax[p]); ay[p] = ffma2(ry, w, ay[p]); az[p] = ffma2(rz, w, az[p]);
+        if (VAR == 0) { ax[p] = ffma2(rx, w, ax[p]); ay[p] = ffma2(ry, w, ay[p]); az[p] = ffma2(rz, w, az[p]); }
+        if (VAR == 1) { ax[p] = ffma2(rx, rx, ax[p]); ay[p] = ffma2(ry, ry, ay[p]); az[p] = ffma2(w, w, az[p]); }
+        if (VAR == 2) { ax[p] = fadd2(ax[p], w); ay[p] = fadd2(ay[p], rx); az[p] = fadd2(az[p], fadd2(ry, rz)); }
+        if (VAR == 3) { ax[p] = ffma2(w, rx, ax[p]); ay[p] = ffma2(w, ry, ay[p]); az[p] = ffma2(w, rz, az[p]); }
       }
     }
     if (SRC == 2) { tile[warp][buf ^ 1][lane] = nxt; __syncwarp(); }
@@ -249,8 +252,9 @@ int main() {
     int block = 128, grid = 148 * wps;
     double c;
 #define BODYM(NP, SRC, label) BODYMX(NP, SRC, true, 0, 8, label)
-#define BODYMX(NP, SRC, MU, PF, UU, label)                                                                              \
-  c = run([&] { k_body_mem<NP, SRC, MU, PF, UU><<<grid, block>>>(d_out, d_pos, iters, 1e-7f, d_cyc); }, grid, block); \
+#define BODYMX(NP, SRC, MU, PF, UU, label) BODYMV(NP, SRC, MU, PF, UU, 0, label)
+#define BODYMV(NP, SRC, MU, PF, UU, VV, label)                                                                              \
+  c = run([&] { k_body_mem<NP, SRC, MU, PF, UU, VV><<<grid, block>>>(d_out, d_pos, iters, 1e-7f, d_cyc); }, grid, block); \
   printf("warps/SMSP=%d %-22s cycles/j=%7.2f  inter/clk/SM=%6.3f  (%%of 10.667 pipe bound: %5.1f)\n", wps, label, \
          c / iters, 4.0 * wps * 32 * 2 * NP * iters / c, 100.0 * (4.0 * wps * 32 * 2 * NP * iters / c) / 10.6667);
     BODYM(1, 0, "R=2 LDS")
@@ -268,6 +272,11 @@ int main() {
     BODYMX(2, 2, true, 0, 4, "R=4 refill U4")
     BODYMX(2, 2, true, 0, 16, "R=4 refill U16")
     BODYMX(2, 2, true, 0, 32, "R=4 refill U32")
+    BODYMV(2, 0, true, 0, 32, 0, "V0 R=4 U32 baseline")
+    BODYMV(2, 0, true, 0, 32, 1, "V1 acc 2-operand")
+    BODYMV(2, 0, true, 0, 32, 2, "V2 acc as FADD2")
+    BODYMV(2, 0, true, 0, 32, 3, "V3 acc w in slot A")
+    BODYMV(2, 0, false, 0, 32, 1, "V1 noMUFU")
     BODYM(1, 3, "R=2 dupLDS")
     BODYM(2, 3, "R=4 dupLDS")
     BODYM(3, 3, "R=6 dupLDS")
