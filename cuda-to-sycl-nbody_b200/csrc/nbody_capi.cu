@@ -57,6 +57,9 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -78,6 +81,8 @@ int load_nccl() {
   SYM(CommInitRank, "ncclCommInitRank")
   SYM(CommDestroy, "ncclCommDestroy")
   SYM(Broadcast, "ncclBroadcast")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(AllGather, "ncclAllGather")
   SYM(GroupStart, "ncclGroupStart")
   SYM(GroupEnd, "ncclGroupEnd")
   SYM(GetErrorString, "ncclGetErrorString")
@@ -109,6 +114,12 @@ struct DeviceCtx {
   ncclComm_t nccl = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_computed = nullptr, ev_comm_done = nullptr;
   std::vector<cudaEvent_t> chunk_ready;
+  // peer-push exchange: every rank's two position replicas as seen from this device
+  // (own pointers, cudaDeviceEnablePeerAccess mappings, or cudaIpcOpenMemHandle mappings)
+  std::vector<float4 *> peer_pos[2];
+  std::vector<void *> ipc_opened;
+  cudaEvent_t iter_done[2] = {nullptr, nullptr};
+  float *barrier_word = nullptr;  // 1 float, NCCL all-reduce used as a device-side barrier (rank mode)
   nbody::KernelConfig cfg{};
   std::string name;
 };
@@ -124,6 +135,8 @@ struct nbody_handle {
   int cur = 0;                        // index of the position buffer holding the current state
   bool replicas_fresh = true;         // current positions complete on every device, no pending events
   bool has_mass = false;
+  int exchange = 0;  // 0 = chunked NCCL broadcasts, 1 = peer push from the kernel epilogue
+  uint64_t iter_count = 0;
   int kernel = NBODY_KERNEL_AUTO;
   float last_ms = 0.0f, last_dev_ms = 0.0f;
   uint64_t launches = 0;
@@ -224,10 +237,16 @@ int enqueue_pass(nbody_handle *h, int src, int flags_last, bool wait_chunks) {
     a.dt = h->p.dt;
     a.G = h->p.G;
     a.damping = h->p.damping;
-    if (h->world == 1) {
+    a.n_peers = 0;
+    if (h->world == 1 || h->exchange == 1) {
+      // one launch over all j.  Peer push: the epilogue stores the new positions into every
+      // other rank's next-position replica as well (not for the accel dump, which moves nothing)
       a.j_begin = 0;
       a.j_end = h->n;
       a.flags = nbody::kFirstChunk | flags_last;
+      if (h->world > 1 && !(flags_last & nbody::kAccelOut))
+        for (int r = 0; r < h->world; r++)
+          if (r != d.rank) a.peer_next[a.n_peers++] = d.peer_pos[src ^ 1][r];
       CK(nbody::launch_step(d.cfg, a, d.compute));
       h->launches++;
       continue;
@@ -319,6 +338,106 @@ int read_sharded(nbody_handle *h, int which /*0 = vel, 1 = acc*/, float *x, floa
   return sync_all(h);
 }
 
+
+// Chooses how new positions reach the other GPUs each iteration and maps peer memory.
+//   NBODY_EXCHANGE=p2p  : peer push -- the integrate epilogue stores into every GPU's replica over
+//                         NVLink (single process: cudaDeviceEnablePeerAccess; one process per GPU:
+//                         CUDA IPC handles exchanged with one ncclAllGather), one launch per iteration,
+//                         a device-side barrier between iterations, no data-path collective
+//   NBODY_EXCHANGE=nccl : rank-ordered ncclBroadcast per iteration, overlapped with the j-chunk kernels
+//   unset / auto        : p2p when every pair of GPUs has peer access, else nccl
+int setup_exchange(nbody_handle *h) {
+  const char *env = getenv("NBODY_EXCHANGE");
+  const bool want_nccl = env && !strcmp(env, "nccl");
+  const bool want_p2p = env && !strcmp(env, "p2p");
+  const bool single_process = (int)h->devs.size() == h->world;
+  const bool rank_mode = h->devs.size() == 1 && h->world > 1;
+  h->exchange = 0;
+  if (want_nccl || (!single_process && !rank_mode)) return 0;
+
+  if (single_process) {
+    for (auto &d : h->devs)
+      for (auto &e : h->devs) {
+        if (d.device == e.device) continue;
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, d.device, e.device));
+        if (!can) {
+          if (want_p2p) return fail(NBODY_E_INVALID, "NBODY_EXCHANGE=p2p but device %d cannot access device %d", d.device, e.device);
+          return 0;
+        }
+      }
+    for (auto &d : h->devs) {
+      CK(cudaSetDevice(d.device));
+      for (auto &e : h->devs) {
+        if (d.device == e.device) continue;
+        cudaError_t pe = cudaDeviceEnablePeerAccess(e.device, 0);
+        if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (pe != cudaSuccess) return fail((int)pe, "cudaDeviceEnablePeerAccess(%d -> %d): %s", d.device, e.device, cudaGetErrorString(pe));
+      }
+      for (int b = 0; b < 2; b++) {
+        d.peer_pos[b].assign(h->world, nullptr);
+        for (auto &e : h->devs) d.peer_pos[b][e.rank] = e.pos[b];
+      }
+      for (int b = 0; b < 2; b++) CK(cudaEventCreateWithFlags(&d.iter_done[b], cudaEventDisableTiming));
+    }
+    h->exchange = 1;
+    return 0;
+  }
+
+  // one process per GPU: exchange CUDA IPC handles of the two replicas through NCCL
+  DeviceCtx &d = h->devs[0];
+  CK(cudaSetDevice(d.device));
+  struct Handles { cudaIpcMemHandle_t mem[2]; int ok; int pad[15]; };
+  static_assert(sizeof(Handles) % 16 == 0, "all-gather payload alignment");
+  Handles mine;
+  memset(&mine, 0, sizeof mine);
+  mine.ok = 1;
+  for (int b = 0; b < 2; b++)
+    if (cudaIpcGetMemHandle(&mine.mem[b], d.pos[b]) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+  Handles *dev_all = nullptr;
+  std::vector<Handles> all(h->world);
+  CK(cudaMalloc(&dev_all, sizeof(Handles) * h->world));
+  CK(cudaMemcpyAsync(dev_all + d.rank, &mine, sizeof mine, cudaMemcpyHostToDevice, d.comm));
+  NK(g_nccl.AllGather(dev_all + d.rank, dev_all, sizeof(Handles), ncclChar, d.nccl, d.comm));
+  CK(cudaMemcpyAsync(all.data(), dev_all, sizeof(Handles) * h->world, cudaMemcpyDeviceToHost, d.comm));
+  CK(cudaStreamSynchronize(d.comm));
+  CK(cudaFree(dev_all));
+  int ok = 1;
+  for (auto &a : all) ok &= a.ok;
+  for (int b = 0; b < 2; b++) d.peer_pos[b].assign(h->world, nullptr);
+  for (int r = 0; r < h->world && ok; r++) {
+    for (int b = 0; b < 2 && ok; b++) {
+      if (r == d.rank) { d.peer_pos[b][r] = d.pos[b]; continue; }
+      void *p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r].mem[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+        break;
+      }
+      d.ipc_opened.push_back(p);
+      d.peer_pos[b][r] = (float4 *)p;
+    }
+  }
+  // every rank must take the same decision: agree with a MIN all-reduce
+  float *flag = nullptr;
+  CK(cudaMalloc(&flag, sizeof(float)));
+  float fv = ok ? 1.0f : 0.0f;
+  CK(cudaMemcpyAsync(flag, &fv, sizeof fv, cudaMemcpyHostToDevice, d.comm));
+  NK(g_nccl.AllReduce(flag, flag, 1, ncclFloat, ncclMin, d.nccl, d.comm));
+  CK(cudaMemcpyAsync(&fv, flag, sizeof fv, cudaMemcpyDeviceToHost, d.comm));
+  CK(cudaStreamSynchronize(d.comm));
+  d.barrier_word = flag;
+  if (fv < 0.5f) {
+    for (void *p : d.ipc_opened) cudaIpcCloseMemHandle(p);
+    d.ipc_opened.clear();
+    cudaGetLastError();
+    if (want_p2p) return fail(NBODY_E_INVALID, "NBODY_EXCHANGE=p2p but CUDA IPC peer mapping is not available between all ranks");
+    return 0;
+  }
+  h->exchange = 1;
+  return 0;
+}
+
 int create_common(const nbody_params *p, const std::vector<int> &devices, int first_rank, int world,
                   const ncclUniqueId *uid, nbody_handle **out) {
   if (!p || !out) return fail(NBODY_E_INVALID, "null argument");
@@ -369,6 +488,10 @@ int create_common(const nbody_params *p, const std::vector<int> &devices, int fi
       nbody_destroy(h);
       return rc2;
     }
+  }
+  if (world > 1) {
+    int rc = setup_exchange(h);
+    if (rc) { nbody_destroy(h); return rc; }
   }
   refresh_configs(h);
   *out = h;
@@ -474,6 +597,10 @@ int nbody_destroy(nbody_handle *h) {
     cudaFree(d.acc);
     cudaFree(d.gather);
     cudaFree(d.mass);
+    cudaFree(d.barrier_word);
+    for (void *p : d.ipc_opened) cudaIpcCloseMemHandle(p);
+    for (cudaEvent_t e : d.iter_done)
+      if (e) cudaEventDestroy(e);
     for (int k = 0; k < 3; k++) cudaFree(d.stage[k]);
     for (cudaEvent_t e : {d.ev_start, d.ev_stop, d.ev_computed, d.ev_comm_done})
       if (e) cudaEventDestroy(e);
@@ -501,7 +628,13 @@ int nbody_set_kernel(nbody_handle *h, int kernel) {
 
 const char *nbody_kernel_name(nbody_handle *h) {
   if (!h || h->devs.empty()) return "";
-  return nbody::config_name(h->devs[0].cfg, h->kname, sizeof h->kname);
+  char base[96];
+  nbody::config_name(h->devs[0].cfg, base, sizeof base);
+  if (h->world > 1)
+    snprintf(h->kname, sizeof h->kname, "%s|x%d:%s", base, h->world, h->exchange == 1 ? "peer-push" : "nccl-bcast");
+  else
+    snprintf(h->kname, sizeof h->kname, "%s", base);
+  return h->kname;
 }
 
 int nbody_set_state(nbody_handle *h, const float *x, const float *y, const float *z, const float *vx,
@@ -539,7 +672,27 @@ int nbody_step(nbody_handle *h) {
     int rc = enqueue_pass(h, h->cur, nbody::kLastChunk, !h->replicas_fresh);
     if (rc) return rc;
     h->cur ^= 1;
-    if (h->world > 1) {
+    if (h->world > 1 && h->exchange == 1) {
+      // peer push: the kernels already delivered the shards; what is left is the barrier that
+      // keeps iteration t+1 (which overwrites the buffer iteration t read) behind every GPU's t
+      const int slot = (int)(h->iter_count & 1);
+      if ((int)h->devs.size() == h->world) {
+        for (auto &d : h->devs) {
+          CK(cudaSetDevice(d.device));
+          CK(cudaEventRecord(d.iter_done[slot], d.compute));
+        }
+        for (auto &d : h->devs) {
+          CK(cudaSetDevice(d.device));
+          for (auto &e : h->devs)
+            if (e.device != d.device) CK(cudaStreamWaitEvent(d.compute, e.iter_done[slot], 0));
+        }
+      } else {
+        DeviceCtx &d = h->devs[0];
+        CK(cudaSetDevice(d.device));
+        NK(g_nccl.AllReduce(d.barrier_word, d.barrier_word, 1, ncclFloat, ncclMin, d.nccl, d.compute));
+      }
+      h->iter_count++;
+    } else if (h->world > 1) {
       for (auto &d : h->devs) {
         CK(cudaSetDevice(d.device));
         CK(cudaEventRecord(d.ev_computed, d.compute));
@@ -552,7 +705,7 @@ int nbody_step(nbody_handle *h) {
   }
   for (auto &d : h->devs) {
     CK(cudaSetDevice(d.device));
-    if (h->world > 1 && iters > 0) {
+    if (h->world > 1 && iters > 0 && h->exchange == 0) {
       CK(cudaEventRecord(d.ev_comm_done, d.comm));
       CK(cudaStreamWaitEvent(d.compute, d.ev_comm_done, 0));
     }
@@ -651,6 +804,7 @@ int nbody_launch_step_device(const nbody_params *p, const void *pos4, void *vel4
   a.G = p->G;
   a.damping = p->damping;
   a.flags = nbody::kFirstChunk | nbody::kLastChunk;
+  a.n_peers = 0;
   CK(nbody::launch_step(cfg, a, (cudaStream_t)cuda_stream));
   return 0;
 }

@@ -88,6 +88,26 @@ __device__ __forceinline__ void integrate_component(float f, float &v, float &p,
   p = ffma(v, dt, p);
 }
 
+// epilogue of one i-body: carry / dump the force sum, or integrate.  When integrating, the new
+// position goes to this GPU's next-position replica AND, in peer-push mode, straight into every
+// peer GPU's replica with plain stores over NVLink (the position "all-gather" is fused into the
+// kernel: by the time the last warp retires, every GPU already holds this shard).
+__device__ __forceinline__ void finish_body(const StepArgs &a, uint32_t li, float fx, float fy, float fz,
+                                            float4 p) {
+  if (!(a.flags & kLastChunk) || (a.flags & kAccelOut)) {
+    a.acc[li] = make_float4(fx, fy, fz, 0.0f);
+    return;
+  }
+  float4 v = a.vel[li];
+  integrate_component(fx, v.x, p.x, a.dt, a.G, a.damping);
+  integrate_component(fy, v.y, p.y, a.dt, a.G, a.damping);
+  integrate_component(fz, v.z, p.z, a.dt, a.G, a.damping);
+  a.vel[li] = v;
+  const uint32_t gi = a.i_begin + li;
+  a.pos_next[gi] = p;
+  for (int k = 0; k < a.n_peers; k++) a.peer_next[k][gi] = p;
+}
+
 // =============================================================================================
 // packed kernel: R (even) i-bodies per thread, pairs (2p, 2p+1) share one f32x2 lane pair
 // =============================================================================================
@@ -197,17 +217,7 @@ __global__ void __launch_bounds__(BLOCK) force_packed_kernel(const StepArgs a) {
     unpack2(ay[k / 2], fy0, fy1);
     unpack2(az[k / 2], fz0, fz1);
     const float fx = (k & 1) ? fx1 : fx0, fy = (k & 1) ? fy1 : fy0, fz = (k & 1) ? fz1 : fz0;
-    if (!(a.flags & kLastChunk) || (a.flags & kAccelOut)) {
-      a.acc[li] = make_float4(fx, fy, fz, 0.0f);
-    } else {
-      float4 v = a.vel[li];
-      float4 p = own[k];
-      integrate_component(fx, v.x, p.x, a.dt, a.G, a.damping);
-      integrate_component(fy, v.y, p.y, a.dt, a.G, a.damping);
-      integrate_component(fz, v.z, p.z, a.dt, a.G, a.damping);
-      a.vel[li] = v;
-      a.pos_next[a.i_begin + li] = p;
-    }
+    finish_body(a, li, fx, fy, fz, own[k]);
   }
 }
 
@@ -327,17 +337,7 @@ __global__ void __launch_bounds__(32 * WARPS) force_wstream_kernel(const StepArg
     unpack2(ay[k / 2], fy0, fy1);
     unpack2(az[k / 2], fz0, fz1);
     const float fx = (k & 1) ? fx1 : fx0, fy = (k & 1) ? fy1 : fy0, fz = (k & 1) ? fz1 : fz0;
-    if (!(a.flags & kLastChunk) || (a.flags & kAccelOut)) {
-      a.acc[li] = make_float4(fx, fy, fz, 0.0f);
-    } else {
-      float4 v = a.vel[li];
-      float4 p = own[k];
-      integrate_component(fx, v.x, p.x, a.dt, a.G, a.damping);
-      integrate_component(fy, v.y, p.y, a.dt, a.G, a.damping);
-      integrate_component(fz, v.z, p.z, a.dt, a.G, a.damping);
-      a.vel[li] = v;
-      a.pos_next[a.i_begin + li] = p;
-    }
+    finish_body(a, li, fx, fy, fz, own[k]);
   }
 }
 
@@ -438,17 +438,7 @@ __global__ void __launch_bounds__(BLOCK) force_scalar_kernel(const StepArgs a) {
   for (int k = 0; k < R; k++) {
     const uint32_t li = tile_i + k * BLOCK + tid;
     if (li >= a.i_count) continue;
-    if (!(a.flags & kLastChunk) || (a.flags & kAccelOut)) {
-      a.acc[li] = make_float4(ax[k], ay[k], az[k], 0.0f);
-    } else {
-      float4 v = a.vel[li];
-      float4 p = own[k];
-      integrate_component(ax[k], v.x, p.x, a.dt, a.G, a.damping);
-      integrate_component(ay[k], v.y, p.y, a.dt, a.G, a.damping);
-      integrate_component(az[k], v.z, p.z, a.dt, a.G, a.damping);
-      a.vel[li] = v;
-      a.pos_next[a.i_begin + li] = p;
-    }
+    finish_body(a, li, ax[k], ay[k], az[k], own[k]);
   }
 }
 

@@ -17,6 +17,8 @@ enum StepFlags : int {
   kAccelOut = 4,    // with kLastChunk: write raw force sums to `acc` instead of integrating
 };
 
+constexpr int kMaxPeers = 15;  // up to 16 GPUs per exchange group
+
 struct StepArgs {
   const float4 *pos;  // n float4 (x,y,z,mass): j-bodies and the i-bodies' old positions
   float4 *pos_next;   // n float4; [i_begin, i_begin+i_count) written when integrating
@@ -27,6 +29,10 @@ struct StepArgs {
   uint32_t j_begin, j_end;
   float eps, dt, G, damping;
   int flags;
+  // peer-push exchange: next-position replicas of the OTHER GPUs (NVLink peer / IPC mappings);
+  // the integrate epilogue stores each new position to all of them
+  int n_peers;
+  float4 *peer_next[kMaxPeers];
 };
 
 // self-term handling of the scalar kernels
