@@ -120,6 +120,8 @@ struct DeviceCtx {
   std::vector<void *> ipc_opened;
   cudaEvent_t iter_done[2] = {nullptr, nullptr};
   float *barrier_word = nullptr;  // 1 float, NCCL all-reduce used as a device-side barrier (rank mode)
+  unsigned int *progress = nullptr;  // j-segment hand-off words, one per 64 owned bodies
+  unsigned int epoch = 0;            // running segment counter of this device's launches
   nbody::KernelConfig cfg{};
   std::string name;
 };
@@ -177,6 +179,9 @@ int alloc_device(nbody_handle *h, DeviceCtx &d) {
   CK(cudaMalloc(&d.pos[1], n * sizeof(float4)));
   CK(cudaMalloc(&d.vel, own * sizeof(float4)));
   CK(cudaMalloc(&d.acc, own * sizeof(float4)));
+  const size_t words = own / 64 + 2;
+  CK(cudaMalloc(&d.progress, words * sizeof(unsigned int)));
+  CK(cudaMemset(d.progress, 0, words * sizeof(unsigned int)));
   for (int k = 0; k < 3; k++) CK(cudaMalloc(&d.stage[k], n * sizeof(float)));
   CK(cudaEventCreate(&d.ev_start));
   CK(cudaEventCreate(&d.ev_stop));
@@ -238,6 +243,8 @@ int enqueue_pass(nbody_handle *h, int src, int flags_last, bool wait_chunks) {
     a.G = h->p.G;
     a.damping = h->p.damping;
     a.n_peers = 0;
+    a.progress = d.progress;
+    a.epoch = &d.epoch;
     if (h->world == 1 || h->exchange == 1) {
       // one launch over all j.  Peer push: the epilogue stores the new positions into every
       // other rank's next-position replica as well (not for the accel dump, which moves nothing)
@@ -598,6 +605,7 @@ int nbody_destroy(nbody_handle *h) {
     cudaFree(d.gather);
     cudaFree(d.mass);
     cudaFree(d.barrier_word);
+    cudaFree(d.progress);
     for (void *p : d.ipc_opened) cudaIpcCloseMemHandle(p);
     for (cudaEvent_t e : d.iter_done)
       if (e) cudaEventDestroy(e);
@@ -805,6 +813,8 @@ int nbody_launch_step_device(const nbody_params *p, const void *pos4, void *vel4
   a.damping = p->damping;
   a.flags = nbody::kFirstChunk | nbody::kLastChunk;
   a.n_peers = 0;
+  a.progress = nullptr;
+  a.epoch = nullptr;
   CK(nbody::launch_step(cfg, a, (cudaStream_t)cuda_stream));
   return 0;
 }

@@ -92,10 +92,10 @@ __device__ __forceinline__ void integrate_component(float f, float &v, float &p,
 // position goes to this GPU's next-position replica AND, in peer-push mode, straight into every
 // peer GPU's replica with plain stores over NVLink (the position "all-gather" is fused into the
 // kernel: by the time the last warp retires, every GPU already holds this shard).
-__device__ __forceinline__ void finish_body(const StepArgs &a, uint32_t li, float fx, float fy, float fz,
-                                            float4 p) {
-  if (!(a.flags & kLastChunk) || (a.flags & kAccelOut)) {
-    a.acc[li] = make_float4(fx, fy, fz, 0.0f);
+__device__ __forceinline__ void finish_body(const StepArgs &a, const int flags, uint32_t li, float fx,
+                                            float fy, float fz, float4 p) {
+  if (!(flags & kLastChunk) || (flags & kAccelOut)) {
+    __stcg(&a.acc[li], make_float4(fx, fy, fz, 0.0f));  // L2: the next j-segment may run on another SM
     return;
   }
   float4 v = a.vel[li];
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(BLOCK) force_packed_kernel(const StepArgs a) {
       for (int h = 0; h < 2; h++) {
         uint32_t li = tile_i + (2 * p + h) * BLOCK + tid;
         uint32_t lc = li < a.i_count ? li : a.i_count - 1;
-        c[h] = a.acc[lc];
+        c[h] = __ldcg(&a.acc[lc]);
       }
       ax[p] = pack2(c[0].x, c[1].x);
       ay[p] = pack2(c[0].y, c[1].y);
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(BLOCK) force_packed_kernel(const StepArgs a) {
     unpack2(ay[k / 2], fy0, fy1);
     unpack2(az[k / 2], fz0, fz1);
     const float fx = (k & 1) ? fx1 : fx0, fy = (k & 1) ? fy1 : fy0, fz = (k & 1) ? fz1 : fz0;
-    finish_body(a, li, fx, fy, fz, own[k]);
+    finish_body(a, a.flags, li, fx, fy, fz, own[k]);
   }
 }
 
@@ -233,18 +233,14 @@ __global__ void __launch_bounds__(BLOCK) force_packed_kernel(const StepArgs a) {
 // (see plan_wstream): all SM sub-partitions then keep >= 5-7 warps until the very end, which
 // is what the FMA pipe needs to stay saturated (tools/ubench_fma2.cu, profiles/).
 // =============================================================================================
-template <int R, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS) force_wstream_kernel(const StepArgs a) {
+// one warp's work: R*32 i-bodies starting at shard-local index warp_i, all j of the launch
+template <int R>
+__device__ __forceinline__ void wstream_body(const StepArgs &a, const uint32_t j_begin, const uint32_t j_end,
+                                             const int flags, const uint32_t warp_i, float4 (*tile)[32],
+                                             const int lane) {
   static_assert(R % 2 == 0, "packed kernel pairs i-bodies");
   constexpr int NP = R / 2;
   constexpr int TJ = 32;
-  __shared__ __align__(16) float4 s_tile[WARPS][2][TJ];
-
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const uint32_t warp_i = (blockIdx.x * (uint32_t)WARPS + warp) * (uint32_t)(32 * R);
-  if (warp_i >= a.i_count) return;  // no CTA-wide synchronisation anywhere below
-  float4(*tile)[TJ] = s_tile[warp];
 
   u64 nx[NP], ny[NP], nz[NP];
   u64 ax[NP], ay[NP], az[NP];
@@ -261,7 +257,7 @@ __global__ void __launch_bounds__(32 * WARPS) force_wstream_kernel(const StepArg
     ny[p] = pack2(-own[2 * p].y, -own[2 * p + 1].y);
     nz[p] = pack2(-own[2 * p].z, -own[2 * p + 1].z);
   }
-  if (a.flags & kFirstChunk) {
+  if (flags & kFirstChunk) {
 #pragma unroll
     for (int p = 0; p < NP; p++) ax[p] = ay[p] = az[p] = 0ull;
   } else {
@@ -272,7 +268,7 @@ __global__ void __launch_bounds__(32 * WARPS) force_wstream_kernel(const StepArg
       for (int h = 0; h < 2; h++) {
         uint32_t li = warp_i + (2 * p + h) * 32 + lane;
         uint32_t lc = li < a.i_count ? li : a.i_count - 1;
-        c[h] = a.acc[lc];
+        c[h] = __ldcg(&a.acc[lc]);
       }
       ax[p] = pack2(c[0].x, c[1].x);
       ay[p] = pack2(c[0].y, c[1].y);
@@ -280,12 +276,12 @@ __global__ void __launch_bounds__(32 * WARPS) force_wstream_kernel(const StepArg
     }
   }
   const u64 eps2 = pack2(a.eps, a.eps);
-  const uint32_t nj = a.j_end - a.j_begin;
+  const uint32_t nj = j_end - j_begin;
   const uint32_t ntiles = (nj + TJ - 1) / TJ;
 
   auto fetch = [&](uint32_t t) -> float4 {
-    uint32_t j = a.j_begin + t * TJ + lane;
-    return a.pos[j < a.j_end ? j : a.j_end - 1];
+    uint32_t j = j_begin + t * TJ + lane;
+    return a.pos[j < j_end ? j : j_end - 1];
   };
   auto interact = [&](int buf, int j) {
     const float4 q = tile[buf][j];
@@ -337,7 +333,59 @@ __global__ void __launch_bounds__(32 * WARPS) force_wstream_kernel(const StepArg
     unpack2(ay[k / 2], fy0, fy1);
     unpack2(az[k / 2], fz0, fz1);
     const float fx = (k & 1) ? fx1 : fx0, fy = (k & 1) ? fy1 : fy0, fz = (k & 1) ? fz1 : fz0;
-    finish_body(a, li, fx, fy, fz, own[k]);
+    finish_body(a, flags, li, fx, fy, fz, own[k]);
+  }
+}
+
+template <int R, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 28 / WARPS) force_wstream_kernel(const StepArgs a) {
+  __shared__ __align__(16) float4 s_tile[WARPS][2][32];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t warp_i = (blockIdx.x * (uint32_t)WARPS + warp) * (uint32_t)(32 * R);
+  if (warp_i >= a.i_count) return;  // no CTA-wide synchronisation anywhere
+  wstream_body<R>(a, a.j_begin, a.j_end, a.flags, warp_i, s_tile[warp], lane);
+}
+
+// (28 resident warps per SM = a 72-register budget: the schedule ptxas finds there is the fastest
+// measured -- 60 or 79 registers lose 6-11 %, profiles/r01_tuning_log.txt)
+// j-segmented launch.  A body-group's sweep over j is cut into `segs` consecutive segments that
+// are separate CTAs of the SAME grid: CTA (seg, g) handles group g over segment seg, takes the
+// accumulators from `acc` and hands them on through `acc`, in order -- so the per-body sum is still
+// one FP32 chain over ascending j (bit-exact), but the schedulable unit is `segs` times shorter.
+// Why: with equal units the launch ends with every SM sub-partition holding ~W/2 units of
+// leftovers that finish one by one at falling occupancy; that tail costs ~0.46 unit-times
+// (3.3 % at N = 1M, 6.6 % at 512K bodies, measured) and shrinks in proportion to the unit.
+// Hand-off: CTA (seg, g) spins on progress[g] until CTA (seg-1, g) has published seg.  The
+// predecessor has a lower blockIdx, so it was dispatched earlier and never waits on a later
+// CTA: forward progress is guaranteed (same argument as decoupled look-back scans).
+template <int R, int MINB>
+__global__ void __launch_bounds__(32, MINB) force_wseg_kernel(const StepArgs a, const uint32_t groups,
+                                                        const uint32_t segs, const uint32_t seg_len,
+                                                        unsigned int *progress, const unsigned int epoch) {
+  __shared__ __align__(16) float4 s_tile[2][32];
+  const int lane = threadIdx.x & 31;
+  const uint32_t seg = blockIdx.x / groups;
+  const uint32_t g = blockIdx.x - seg * groups;
+  const uint32_t warp_i = g * (uint32_t)(32 * R);
+  if (warp_i >= a.i_count) return;
+  const uint32_t j_begin = a.j_begin + seg * seg_len;
+  const uint32_t j_end = min(a.j_end, j_begin + seg_len);
+  const int flags = (seg == 0 ? (a.flags & kFirstChunk) : 0) | (seg == segs - 1 ? (a.flags & (kLastChunk | kAccelOut)) : 0);
+  if (seg > 0) {
+    if (lane == 0) {
+      volatile unsigned int *p = progress + g;
+      while (*p != epoch + seg) {
+      }
+      __threadfence();
+    }
+    __syncwarp();
+  }
+  wstream_body<R>(a, j_begin, j_end, flags, warp_i, s_tile, lane);
+  if (seg + 1 < segs) {
+    __threadfence();  // every lane publishes its accumulator stores ...
+    __syncwarp();
+    if (lane == 0) atomicExch(progress + g, epoch + seg + 1);  // ... before the group is handed on
   }
 }
 
@@ -368,7 +416,7 @@ __global__ void __launch_bounds__(BLOCK) force_scalar_kernel(const StepArgs a) {
     if (a.flags & kFirstChunk) {
       ax[k] = ay[k] = az[k] = 0.0f;
     } else {
-      float4 c = a.acc[lc];
+      float4 c = __ldcg(&a.acc[lc]);
       ax[k] = c.x;
       ay[k] = c.y;
       az[k] = c.z;
@@ -438,7 +486,7 @@ __global__ void __launch_bounds__(BLOCK) force_scalar_kernel(const StepArgs a) {
   for (int k = 0; k < R; k++) {
     const uint32_t li = tile_i + k * BLOCK + tid;
     if (li >= a.i_count) continue;
-    finish_body(a, li, ax[k], ay[k], az[k], own[k]);
+    finish_body(a, a.flags, li, ax[k], ay[k], az[k], own[k]);
   }
 }
 
@@ -498,12 +546,18 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
     c = {0, 1, 128, kSelfBranch, sms};
     return c;
   }
-  // family: 3 = warp-streaming packed (AUTO), 1 = CTA-tiled packed, 2 = CTA-tiled scalar
-  int family = requested_kernel == 3 ? 2 : (requested_kernel == 2 ? 1 : 3);
+  // family: 4 = j-segmented warp-streaming packed (AUTO), 3 = unsegmented, 1 = CTA-tiled packed, 2 = CTA-tiled scalar
+  int family = requested_kernel == 3 ? 2 : (requested_kernel == 2 ? 1 : 4);
   int r = 4, block = 128;
-  if (family == 3) {
-    // one warp per CTA; R = 4 i-bodies per lane unless that leaves fewer than ~5 warps per SM
-    // sub-partition, then R = 2 doubles the number of warps
+  if (family == 4) {
+    // one warp per CTA.  Wider register blocking (fewer LDS per interaction, more ILP, fewer
+    // resident warps) as long as the shard still supplies ~2 warps per resident slot:
+    // R = 6 at 14 warps/SM, R = 4 at 20, R = 2 at 28 (measured: profiles/r01_tuning_log.txt)
+    block = 32;
+    r = 6;
+    if ((uint64_t)i_count < (uint64_t)sms * 2700u) r = 4;  // < ~400K bodies on 148 SMs
+    if ((uint64_t)i_count < (uint64_t)sms * 1350u) r = 2;  // < ~200K bodies
+  } else if (family == 3) {
     block = 32;
     if ((uint64_t)i_count < (uint64_t)sms * 20u * 128u) r = 2;
   } else {
@@ -519,7 +573,7 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
     if (got >= 2 && er > 0 && eb > 0) {
       r = er;
       block = eb;
-      if (got == 3 && ef >= 1 && ef <= 3) family = ef;
+      if (got == 3 && ef >= 1 && ef <= 4) family = ef;
     }
   }
   c = {family, r, block, kSelfNone, sms};
@@ -527,7 +581,7 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
 }
 
 const char *config_name(const KernelConfig &c, char *buf, size_t len) {
-  const char *fam = c.family == 1 ? "packed_f32x2" : (c.family == 2 ? "scalar_blocked" : (c.family == 3 ? "wstream_f32x2" : "generic"));
+  const char *fam = c.family == 1 ? "packed_f32x2" : (c.family == 2 ? "scalar_blocked" : (c.family == 3 ? "wstream_f32x2" : (c.family == 4 ? "wseg_f32x2" : "generic")));
   const char *self = c.self_mode == kSelfNone ? "nopred"
                                               : (c.self_mode == kSelfBranch ? "branch" : "predicated");
   snprintf(buf, len, "%s_r%d_b%d_%s", fam, c.r, c.block, self);
@@ -553,33 +607,52 @@ static cudaError_t launch_scalar(const StepArgs &a, cudaStream_t s) {
 // makes every generation equally full instead of leaving a thin last one (e.g. 55.4 CTAs/SM
 // -> 28 + 27.4 rather than 32 + 23.4).  The cap is enforced with dynamic shared memory.
 struct WstreamPlan {
-  int k_cap;          // resident CTAs per SM to aim for
-  size_t dyn_smem;    // dynamic shared memory per CTA that enforces it
+  int k_cap = 0;        // resident CTAs per SM to aim for
+  size_t dyn_smem = 0;  // dynamic shared memory per CTA that enforces it
 };
 
-template <int R, int WARPS>
-static cudaError_t plan_wstream(uint32_t ctas, int sms, WstreamPlan *plan) {
-  auto kern = force_wstream_kernel<R, WARPS>;
-  // function attributes are per device: a single process may drive several GPUs
-  static bool attr_done[64] = {false};
+// per (kernel, device): attributes set once, last plan cached (a process may drive several GPUs)
+struct PlanSlot {
+  const void *kern = nullptr;
+  int dev = -1;
+  uint32_t ctas = 0;
+  int sms = 0;
+  WstreamPlan plan;
+};
+static PlanSlot g_plan_slots[256];
+static int g_plan_slot_count = 0;
+
+static cudaError_t plan_resident(const void *kern, int threads, uint32_t ctas, int sms, WstreamPlan *out) {
   cudaError_t e;
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  if (!attr_done[dev]) {
+  PlanSlot *slot = nullptr;
+  for (int i = 0; i < g_plan_slot_count; i++)
+    if (g_plan_slots[i].kern == kern && g_plan_slots[i].dev == dev) slot = &g_plan_slots[i];
+  if (!slot) {
+    if (g_plan_slot_count >= 256) return cudaErrorMemoryAllocation;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
-    attr_done[dev] = true;
+    slot = &g_plan_slots[g_plan_slot_count++];
+    slot->kern = kern;
+    slot->dev = dev;
+  }
+  if (slot->ctas == ctas && slot->sms == sms && slot->plan.k_cap > 0) {
+    *out = slot->plan;
+    return cudaSuccess;
   }
   int k_max = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k_max, kern, 32 * WARPS, 0)) != cudaSuccess) return e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k_max, kern, threads, 0)) != cudaSuccess) return e;
   if (k_max < 1) return cudaErrorInvalidConfiguration;
-  const double per_sm = (double)ctas / sms;
-  int gens = (int)ceil(per_sm / k_max);
-  if (gens < 1) gens = 1;
-  int k = (int)ceil(per_sm / gens);
-  if (k > k_max) k = k_max;
-  if (k < 1) k = 1;
+  int k = k_max;  // ctas == 0: no cap (grids whose CTAs differ in size drain as one queue)
+  if (ctas > 0) {
+    const double per_sm = (double)ctas / sms;
+    int gens = (int)ceil(per_sm / k_max);
+    if (gens < 1) gens = 1;
+    k = (int)ceil(per_sm / gens);
+    if (k > k_max) k = k_max;
+    if (k < 1) k = 1;
+  }
   if (const char *env = getenv("NBODY_RESIDENT_CTAS")) {  // tuning override
     int v = atoi(env);
     if (v >= 1 && v <= k_max) k = v;
@@ -591,16 +664,19 @@ static cudaError_t plan_wstream(uint32_t ctas, int sms, WstreamPlan *plan) {
     while (hi - lo > 256) {
       size_t mid = (lo + hi) / 2;
       int occ = 0;
-      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * WARPS, mid)) != cudaSuccess) return e;
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, mid)) != cudaSuccess) return e;
       if (occ >= k) lo = mid; else hi = mid;
     }
     dyn = lo;
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * WARPS, dyn);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, dyn);
     if (occ != k) dyn = 0;  // cannot hit k exactly: leave the hardware limit
   }
-  plan->k_cap = k;
-  plan->dyn_smem = dyn;
+  slot->ctas = ctas;
+  slot->sms = sms;
+  slot->plan.k_cap = k;
+  slot->plan.dyn_smem = dyn;
+  *out = slot->plan;
   return cudaSuccess;
 }
 
@@ -608,20 +684,41 @@ template <int R, int WARPS>
 static cudaError_t launch_wstream(const StepArgs &a, int sms, cudaStream_t s) {
   const uint32_t warps = (a.i_count + 32 * R - 1) / (32 * R);
   const uint32_t ctas = (warps + WARPS - 1) / WARPS;
-  // the plan depends on (device, ctas): cache the last one per device and instantiation
-  struct Cached { uint32_t ctas = 0; int sms = 0; WstreamPlan plan{}; };
-  static Cached cache[64];
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
+  WstreamPlan plan;
+  cudaError_t e = plan_resident((const void *)force_wstream_kernel<R, WARPS>, 32 * WARPS, ctas, sms, &plan);
   if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  Cached &c = cache[dev];
-  if (c.ctas != ctas || c.sms != sms) {
-    if ((e = plan_wstream<R, WARPS>(ctas, sms, &c.plan)) != cudaSuccess) return e;
-    c.ctas = ctas;
-    c.sms = sms;
+  force_wstream_kernel<R, WARPS><<<ctas, 32 * WARPS, plan.dyn_smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+// segment planning: aim at ~16 schedulable units per resident warp slot
+static uint32_t plan_segments(uint32_t groups, uint32_t nj, int sms, int k_max) {
+  if (const char *env = getenv("NBODY_SEGS")) {  // tuning override
+    int v = atoi(env);
+    if (v >= 1 && v <= 1024) return (uint32_t)v;
   }
-  force_wstream_kernel<R, WARPS><<<ctas, 32 * WARPS, c.plan.dyn_smem, s>>>(a);
+  const double gens = (double)groups / ((double)sms * k_max);
+  int segs = (int)ceil(16.0 / (gens > 0.05 ? gens : 0.05));
+  if (segs > 64) segs = 64;
+  while (segs > 1 && nj / segs < 4096) segs--;  // keep segments long: hand-off cost stays invisible
+  return (uint32_t)(segs < 1 ? 1 : segs);
+}
+
+template <int R, int MINB>
+static cudaError_t launch_wseg_mb(const StepArgs &a, int sms, unsigned int *progress, unsigned int *epoch,
+                                  cudaStream_t s) {
+  const uint32_t groups = (a.i_count + 32 * R - 1) / (32 * R);
+  int k_max = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k_max, (const void *)force_wseg_kernel<R, MINB>, 32, 0);
+  if (e != cudaSuccess) return e;
+  const uint32_t nj = a.j_end - a.j_begin;
+  uint32_t segs = plan_segments(groups, nj, sms, k_max);
+  uint32_t seg_len = ((nj + segs - 1) / segs + 31u) / 32u * 32u;
+  segs = (nj + seg_len - 1) / seg_len;
+  if (*epoch > 0xf0000000u) return cudaErrorInvalidValue;  // 4e9 segment-launches: recreate the handle
+  const unsigned int ep = *epoch;
+  *epoch += segs;
+  force_wseg_kernel<R, MINB><<<groups * segs, 32, 0, s>>>(a, groups, segs, seg_len, progress, ep);
   return cudaGetLastError();
 }
 
@@ -641,6 +738,17 @@ cudaError_t launch_step(const KernelConfig &c, const StepArgs &a, cudaStream_t s
   NB_WSTREAM(4, 2)
   NB_WSTREAM(4, 4)
 #undef NB_WSTREAM
+  if (c.family == 4 && a.acc && a.progress && a.epoch) {  // j-segmented warp-streaming launch
+    // (R, resident warps per SM promised to ptxas): the three tuned points, profiles/r01_tuning_log.txt
+    if (c.r == 2) return launch_wseg_mb<2, 28>(a, c.sms, a.progress, a.epoch, s);
+    if (c.r == 4) return launch_wseg_mb<4, 20>(a, c.sms, a.progress, a.epoch, s);
+    if (c.r == 6) return launch_wseg_mb<6, 14>(a, c.sms, a.progress, a.epoch, s);
+  }
+  if (c.family == 4) {  // no hand-off buffers (caller-owned memory entry): plain warp-streaming
+    if (c.r == 2) return launch_wstream<2, 1>(a, c.sms, s);
+    if (c.r == 4) return launch_wstream<4, 1>(a, c.sms, s);
+    if (c.r == 6) return launch_wstream<6, 1>(a, c.sms, s);
+  }
 #define NB_PACKED(RR, BB) \
   if (c.family == 1 && c.r == RR && c.block == BB) return launch_packed<RR, BB>(a, s);
 #define NB_SCALAR(RR, BB) \

@@ -33,6 +33,10 @@ struct StepArgs {
   // the integrate epilogue stores each new position to all of them
   int n_peers;
   float4 *peer_next[kMaxPeers];
+  // j-segmented launches (host-side launch state, ignored by the kernels): per-group hand-off
+  // words (one per 64 owned bodies) and the handle's running epoch counter
+  unsigned int *progress;
+  unsigned int *epoch;
 };
 
 // self-term handling of the scalar kernels
@@ -44,7 +48,8 @@ enum SelfMode : int {
 
 struct KernelConfig {
   int family;  // 0 = generic scalar (R=1, predicated), 1 = CTA-tiled packed f32x2,
-               // 2 = CTA-tiled scalar blocked, 3 = warp-streaming packed f32x2 (production)
+               // 2 = CTA-tiled scalar blocked, 3 = warp-streaming packed f32x2,
+               // 4 = warp-streaming packed f32x2 with j-segmented hand-off (production)
   int r;       // i-bodies per thread
   int block;   // threads per CTA
   int self_mode;
