@@ -190,7 +190,7 @@ def cpu_baseline(n_bodies: int, target_s: float = 12.0):
             "seconds": t, "host_cpus": os.cpu_count()}
 
 
-def run_reference_arm(args, dist):
+def run_reference_arm(args, dist, emit):
     """--impl reference: the CPU port on all host threads, rank 0 only."""
     if dist.rank != 0:
         return
@@ -220,10 +220,10 @@ def run_reference_arm(args, dist):
             "cpu_baseline": {"value": g, "unit": "G inter/s", "cores": o.num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": g, "unit": "G inter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
-def run_b200_arm(args, dist):
+def run_b200_arm(args, dist, emit):
     import numpy as np
     import torch
 
@@ -365,10 +365,19 @@ def run_b200_arm(args, dist):
                                                  "what": "unmodified particle_interaction<BRANCH> (oracle/_ref), gwSize 64, same GPU, same N"}
         except Exception as e:  # noqa: BLE001
             line["reference_cuda_kernel"] = {"error": str(e)}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else any library prints there (NCCL's version
+    # banner, torchrun notices) is sent to stderr by pointing fd 1 at fd 2 for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -381,13 +390,13 @@ def main():
     if args.impl == "reference":
         dist = Dist(backend="gloo")
         try:
-            run_reference_arm(args, dist)
+            run_reference_arm(args, dist, emit)
         finally:
             dist.close()
         return
     dist = Dist()
     try:
-        run_b200_arm(args, dist)
+        run_b200_arm(args, dist, emit)
     finally:
         dist.close()
 
