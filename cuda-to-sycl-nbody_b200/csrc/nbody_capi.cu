@@ -162,7 +162,7 @@ void plan_shards(nbody_handle *h) {
 
 void refresh_configs(nbody_handle *h) {
   for (auto &d : h->devs)
-    d.cfg = nbody::choose_config(h->kernel, h->p.calc_method, h->p.dist_eps, d.i_count, d.sms);
+    d.cfg = nbody::choose_config(h->kernel, h->p.calc_method, h->p.dist_eps, d.i_count, d.sms, h->has_mass);
 }
 
 int alloc_device(nbody_handle *h, DeviceCtx &d) {
@@ -629,6 +629,8 @@ int nbody_set_kernel(nbody_handle *h, int kernel) {
       (h->p.calc_method != NBODY_CALC_BRANCH || !nbody::eps_allows_unpredicated(h->p.dist_eps)))
     return fail(NBODY_E_INVALID,
                 "unpredicated kernels are not bit-exact for this distEps / calcMethod; use AUTO or GENERIC");
+  if ((kernel == NBODY_KERNEL_PACKED || kernel == NBODY_KERNEL_SCALAR) && h->has_mass)
+    return fail(NBODY_E_STATE, "per-body masses need the AUTO or GENERIC kernel");
   h->kernel = kernel;
   refresh_configs(h);
   return 0;
@@ -655,6 +657,10 @@ int nbody_set_state(nbody_handle *h, const float *x, const float *y, const float
     CK(cudaSetDevice(d.device));
     rc = upload_soa(h, d, x, y, z, nullptr, 1.0f, d.pos[0], 0, h->n);
     if (rc) return rc;
+    if (h->has_mass) {  // masses set earlier stay with their bodies
+      CK(nbody::launch_set_w(d.pos[0], d.mass, 1.0f, h->n, d.compute));
+      h->launches++;
+    }
     // the staging arrays are reused for the velocities: same stream, so ordered after the interleave
     rc = upload_soa(h, d, vx, vy, vz, nullptr, 0.0f, d.vel, d.i_begin, d.i_count);
     if (rc) return rc;
@@ -665,7 +671,22 @@ int nbody_set_state(nbody_handle *h, const float *x, const float *y, const float
 
 int nbody_set_mass(nbody_handle *h, const float *m) {
   if (!h) return fail(NBODY_E_INVALID, "null handle");
-  return fail(NBODY_E_STATE, "per-body masses are not implemented in this build (unit mass only)");
+  if (m && (h->kernel == NBODY_KERNEL_PACKED || h->kernel == NBODY_KERNEL_SCALAR))
+    return fail(NBODY_E_STATE, "per-body masses need the AUTO or GENERIC kernel");
+  int rc = sync_all(h);
+  if (rc) return rc;
+  for (auto &d : h->devs) {
+    CK(cudaSetDevice(d.device));
+    if (m) {
+      if (!d.mass) CK(cudaMalloc(&d.mass, (size_t)h->n * sizeof(float)));
+      CK(cudaMemcpyAsync(d.mass, m, (size_t)h->n * sizeof(float), cudaMemcpyHostToDevice, d.compute));
+    }
+    CK(nbody::launch_set_w(d.pos[h->cur], m ? d.mass : nullptr, 1.0f, h->n, d.compute));
+    h->launches++;
+  }
+  h->has_mass = m != nullptr;
+  refresh_configs(h);
+  return sync_all(h);
 }
 
 int nbody_step(nbody_handle *h) {
@@ -780,6 +801,70 @@ int nbody_compute_accel(nbody_handle *h, float *ax, float *ay, float *az) {
   return read_sharded(h, 1, ax, ay, az, nullptr);
 }
 
+namespace {
+struct CkptHeader {
+  char magic[8];
+  uint64_t n;
+  float G, dt, damping, dist_eps;
+  int32_t iters_per_frame, calc_method, has_mass, reserved;
+};
+const char kCkptMagic[8] = {'N', 'B', 'B', '2', '0', '0', 0, 1};
+}  // namespace
+
+int nbody_save_state(nbody_handle *h, const char *path) {
+  if (!h || !path) return fail(NBODY_E_INVALID, "null argument");
+  const size_t n = h->n;
+  std::vector<float> buf(7 * n);
+  int rc = nbody_read_pos(h, &buf[0], &buf[n], &buf[2 * n]);
+  if (!rc) rc = nbody_read_vel(h, &buf[3 * n], &buf[4 * n], &buf[5 * n]);
+  if (rc) return rc;
+  if (h->has_mass) {
+    std::vector<float> p4(4 * n);
+    if ((rc = nbody_read_pos_f4(h, p4.data()))) return rc;
+    for (size_t i = 0; i < n; i++) buf[6 * n + i] = p4[4 * i + 3];
+  }
+  CkptHeader hd;
+  memset(&hd, 0, sizeof hd);
+  memcpy(hd.magic, kCkptMagic, 8);
+  hd.n = n;
+  hd.G = h->p.G;
+  hd.dt = h->p.dt;
+  hd.damping = h->p.damping;
+  hd.dist_eps = h->p.dist_eps;
+  hd.iters_per_frame = h->p.iters_per_frame;
+  hd.calc_method = h->p.calc_method;
+  hd.has_mass = h->has_mass ? 1 : 0;
+  FILE *f = fopen(path, "wb");
+  if (!f) return fail(NBODY_E_INVALID, "cannot open %s for writing", path);
+  const size_t count = (h->has_mass ? 7 : 6) * n;
+  bool ok = fwrite(&hd, sizeof hd, 1, f) == 1 && fwrite(buf.data(), sizeof(float), count, f) == count;
+  ok = (fclose(f) == 0) && ok;
+  return ok ? 0 : fail(NBODY_E_INVALID, "short write to %s", path);
+}
+
+int nbody_load_state(nbody_handle *h, const char *path) {
+  if (!h || !path) return fail(NBODY_E_INVALID, "null argument");
+  FILE *f = fopen(path, "rb");
+  if (!f) return fail(NBODY_E_INVALID, "cannot open %s", path);
+  CkptHeader hd;
+  if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, kCkptMagic, 8) != 0) {
+    fclose(f);
+    return fail(NBODY_E_INVALID, "%s is not an nbody-b200 checkpoint", path);
+  }
+  if (hd.n != h->n) {
+    fclose(f);
+    return fail(NBODY_E_INVALID, "checkpoint holds %llu bodies, handle %u", (unsigned long long)hd.n, h->n);
+  }
+  const size_t n = h->n, count = (hd.has_mass ? 7 : 6) * n;
+  std::vector<float> buf(count);
+  const bool ok = fread(buf.data(), sizeof(float), count, f) == count;
+  fclose(f);
+  if (!ok) return fail(NBODY_E_INVALID, "%s is truncated", path);
+  int rc = nbody_set_mass(h, hd.has_mass ? &buf[6 * n] : nullptr);
+  if (!rc) rc = nbody_set_state(h, &buf[0], &buf[n], &buf[2 * n], &buf[3 * n], &buf[4 * n], &buf[5 * n]);
+  return rc;
+}
+
 const char *nbody_device_name(nbody_handle *h) { return (h && !h->devs.empty()) ? h->devs[0].name.c_str() : "Unknown Device"; }
 uint64_t nbody_num_particles(nbody_handle *h) { return h ? h->n : 0; }
 int nbody_num_gpus(nbody_handle *h) { return h ? (int)h->devs.size() : 0; }
@@ -796,7 +881,7 @@ int nbody_launch_step_device(const nbody_params *p, const void *pos4, void *vel4
   if ((kernel == NBODY_KERNEL_PACKED || kernel == NBODY_KERNEL_SCALAR) &&
       (p->calc_method != NBODY_CALC_BRANCH || !nbody::eps_allows_unpredicated(p->dist_eps)))
     return fail(NBODY_E_INVALID, "unpredicated kernels are not bit-exact for this distEps / calcMethod");
-  nbody::KernelConfig cfg = nbody::choose_config(kernel, p->calc_method, p->dist_eps, (uint32_t)i_count, sms);
+  nbody::KernelConfig cfg = nbody::choose_config(kernel, p->calc_method, p->dist_eps, (uint32_t)i_count, sms, false);
   nbody::StepArgs a;
   a.pos = (const float4 *)pos4;
   a.pos_next = (float4 *)pos4_next;

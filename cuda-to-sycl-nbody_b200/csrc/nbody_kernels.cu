@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(BLOCK) force_packed_kernel(const StepArgs a) {
 // is what the FMA pipe needs to stay saturated (tools/ubench_fma2.cu, profiles/).
 // =============================================================================================
 // one warp's work: R*32 i-bodies starting at shard-local index warp_i, all j of the launch
-template <int R>
+template <int R, bool MASS>
 __device__ __forceinline__ void wstream_body(const StepArgs &a, const uint32_t j_begin, const uint32_t j_end,
                                              const int flags, const uint32_t warp_i, float4 (*tile)[32],
                                              const int lane) {
@@ -300,6 +300,7 @@ __device__ __forceinline__ void wstream_body(const StepArgs &a, const uint32_t j
       float c0, c1;
       unpack2(c, c0, c1);
       u64 w = pack2(frsq(c0), frsq(c1));
+      if (MASS) w = fmul2(w, pack2(q.w, q.w));  // extension: per-body mass m_j (float4.w); m = 1 changes no bit
       ax[p] = ffma2(rx, w, ax[p]);
       ay[p] = ffma2(ry, w, ay[p]);
       az[p] = ffma2(rz, w, az[p]);
@@ -337,14 +338,14 @@ __device__ __forceinline__ void wstream_body(const StepArgs &a, const uint32_t j
   }
 }
 
-template <int R, int WARPS>
+template <int R, int WARPS, bool MASS>
 __global__ void __launch_bounds__(32 * WARPS, 28 / WARPS) force_wstream_kernel(const StepArgs a) {
   __shared__ __align__(16) float4 s_tile[WARPS][2][32];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint32_t warp_i = (blockIdx.x * (uint32_t)WARPS + warp) * (uint32_t)(32 * R);
   if (warp_i >= a.i_count) return;  // no CTA-wide synchronisation anywhere
-  wstream_body<R>(a, a.j_begin, a.j_end, a.flags, warp_i, s_tile[warp], lane);
+  wstream_body<R, MASS>(a, a.j_begin, a.j_end, a.flags, warp_i, s_tile[warp], lane);
 }
 
 // (28 resident warps per SM = a 72-register budget: the schedule ptxas finds there is the fastest
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(32 * WARPS, 28 / WARPS) force_wstream_kernel(c
 // Hand-off: CTA (seg, g) spins on progress[g] until CTA (seg-1, g) has published seg.  The
 // predecessor has a lower blockIdx, so it was dispatched earlier and never waits on a later
 // CTA: forward progress is guaranteed (same argument as decoupled look-back scans).
-template <int R, int MINB>
+template <int R, int MINB, bool MASS>
 __global__ void __launch_bounds__(32, MINB) force_wseg_kernel(const StepArgs a, const uint32_t groups,
                                                         const uint32_t segs, const uint32_t seg_len,
                                                         unsigned int *progress, const unsigned int epoch) {
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(32, MINB) force_wseg_kernel(const StepArgs a, 
     }
     __syncwarp();
   }
-  wstream_body<R>(a, j_begin, j_end, flags, warp_i, s_tile, lane);
+  wstream_body<R, MASS>(a, j_begin, j_end, flags, warp_i, s_tile, lane);
   if (seg + 1 < segs) {
     __threadfence();  // every lane publishes its accumulator stores ...
     __syncwarp();
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(32, MINB) force_wseg_kernel(const StepArgs a, 
 // scalar kernel: R i-bodies per thread, scalar FADD/FMUL/FFMA; also the generic/faithful path
 // (BRANCH predicate for any eps, PREDICATED as shipped)
 // =============================================================================================
-template <int R, int BLOCK, int SELF>
+template <int R, int BLOCK, int SELF, bool MASS>
 __global__ void __launch_bounds__(BLOCK) force_scalar_kernel(const StepArgs a) {
   constexpr int TJ = BLOCK;
   __shared__ __align__(16) float4 s_p[2][TJ];
@@ -444,6 +445,7 @@ __global__ void __launch_bounds__(BLOCK) force_scalar_kernel(const StepArgs a) {
       float c = fmul(d, d);
       c = fmul(d, c);
       float w = frsq(c);
+      if (MASS) w = fmul(w, q.w);  // extension: per-body mass m_j
       if (SELF == kSelfNone) {
         ax[k] = ffma(rx, w, ax[k]);
         ay[k] = ffma(ry, w, ay[k]);
@@ -508,6 +510,18 @@ __global__ void interleave_kernel(const float *__restrict__ x, const float *__re
   dst[i] = make_float4(x[i], y[i], z[i], m ? m[i] : w);
 }
 
+__global__ void set_w_kernel(float4 *__restrict__ pos, const float *__restrict__ m, float w, uint32_t count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  pos[i].w = m ? m[i] : w;
+}
+
+cudaError_t launch_set_w(float4 *pos, const float *m, float w, uint32_t count, cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  set_w_kernel<<<(count + 255) / 256, 256, 0, stream>>>(pos, m, w, count);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_deinterleave(const float4 *src, float *x, float *y, float *z, uint32_t count,
                                 cudaStream_t stream) {
   if (count == 0) return cudaSuccess;
@@ -535,15 +549,15 @@ bool eps_allows_unpredicated(float eps) {
 }
 
 KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uint32_t i_count,
-                           int sms) {
+                           int sms, bool has_mass) {
   KernelConfig c;
   const bool exact_unpred = eps_allows_unpredicated(eps);
   if (calc_method != 0) {  // PREDICATED, as shipped
-    c = {0, 1, 128, kSelfPredicated, sms};
+    c = {0, 1, 128, kSelfPredicated, sms, has_mass ? 1 : 0};
     return c;
   }
   if (requested_kernel == 1 /*GENERIC*/ || !exact_unpred) {
-    c = {0, 1, 128, kSelfBranch, sms};
+    c = {0, 1, 128, kSelfBranch, sms, has_mass ? 1 : 0};
     return c;
   }
   // family: 4 = j-segmented warp-streaming packed (AUTO), 3 = unsegmented, 1 = CTA-tiled packed, 2 = CTA-tiled scalar
@@ -576,7 +590,7 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
       if (got == 3 && ef >= 1 && ef <= 4) family = ef;
     }
   }
-  c = {family, r, block, kSelfNone, sms};
+  c = {family, r, block, kSelfNone, sms, has_mass ? 1 : 0};
   return c;
 }
 
@@ -584,7 +598,7 @@ const char *config_name(const KernelConfig &c, char *buf, size_t len) {
   const char *fam = c.family == 1 ? "packed_f32x2" : (c.family == 2 ? "scalar_blocked" : (c.family == 3 ? "wstream_f32x2" : (c.family == 4 ? "wseg_f32x2" : "generic")));
   const char *self = c.self_mode == kSelfNone ? "nopred"
                                               : (c.self_mode == kSelfBranch ? "branch" : "predicated");
-  snprintf(buf, len, "%s_r%d_b%d_%s", fam, c.r, c.block, self);
+  snprintf(buf, len, "%s_r%d_b%d_%s%s", fam, c.r, c.block, self, c.mass ? "_mass" : "");
   return buf;
 }
 
@@ -594,10 +608,10 @@ static cudaError_t launch_packed(const StepArgs &a, cudaStream_t s) {
   force_packed_kernel<R, BLOCK><<<grid, BLOCK, 0, s>>>(a);
   return cudaGetLastError();
 }
-template <int R, int BLOCK, int SELF>
+template <int R, int BLOCK, int SELF, bool MASS = false>
 static cudaError_t launch_scalar(const StepArgs &a, cudaStream_t s) {
   uint32_t grid = (a.i_count + BLOCK * R - 1) / (BLOCK * R);
-  force_scalar_kernel<R, BLOCK, SELF><<<grid, BLOCK, 0, s>>>(a);
+  force_scalar_kernel<R, BLOCK, SELF, MASS><<<grid, BLOCK, 0, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -680,14 +694,14 @@ static cudaError_t plan_resident(const void *kern, int threads, uint32_t ctas, i
   return cudaSuccess;
 }
 
-template <int R, int WARPS>
+template <int R, int WARPS, bool MASS>
 static cudaError_t launch_wstream(const StepArgs &a, int sms, cudaStream_t s) {
   const uint32_t warps = (a.i_count + 32 * R - 1) / (32 * R);
   const uint32_t ctas = (warps + WARPS - 1) / WARPS;
   WstreamPlan plan;
-  cudaError_t e = plan_resident((const void *)force_wstream_kernel<R, WARPS>, 32 * WARPS, ctas, sms, &plan);
+  cudaError_t e = plan_resident((const void *)force_wstream_kernel<R, WARPS, MASS>, 32 * WARPS, ctas, sms, &plan);
   if (e != cudaSuccess) return e;
-  force_wstream_kernel<R, WARPS><<<ctas, 32 * WARPS, plan.dyn_smem, s>>>(a);
+  force_wstream_kernel<R, WARPS, MASS><<<ctas, 32 * WARPS, plan.dyn_smem, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -704,12 +718,12 @@ static uint32_t plan_segments(uint32_t groups, uint32_t nj, int sms, int k_max) 
   return (uint32_t)(segs < 1 ? 1 : segs);
 }
 
-template <int R, int MINB>
+template <int R, int MINB, bool MASS>
 static cudaError_t launch_wseg_mb(const StepArgs &a, int sms, unsigned int *progress, unsigned int *epoch,
                                   cudaStream_t s) {
   const uint32_t groups = (a.i_count + 32 * R - 1) / (32 * R);
   int k_max = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k_max, (const void *)force_wseg_kernel<R, MINB>, 32, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k_max, (const void *)force_wseg_kernel<R, MINB, MASS>, 32, 0);
   if (e != cudaSuccess) return e;
   const uint32_t nj = a.j_end - a.j_begin;
   uint32_t segs = plan_segments(groups, nj, sms, k_max);
@@ -718,54 +732,48 @@ static cudaError_t launch_wseg_mb(const StepArgs &a, int sms, unsigned int *prog
   if (*epoch > 0xf0000000u) return cudaErrorInvalidValue;  // 4e9 segment-launches: recreate the handle
   const unsigned int ep = *epoch;
   *epoch += segs;
-  force_wseg_kernel<R, MINB><<<groups * segs, 32, 0, s>>>(a, groups, segs, seg_len, progress, ep);
+  force_wseg_kernel<R, MINB, MASS><<<groups * segs, 32, 0, s>>>(a, groups, segs, seg_len, progress, ep);
   return cudaGetLastError();
 }
 
 cudaError_t launch_step(const KernelConfig &c, const StepArgs &a, cudaStream_t s) {
   if (a.i_count == 0) return cudaSuccess;
   if (c.family == 0) {
-    if (c.self_mode == kSelfPredicated) return launch_scalar<1, 128, kSelfPredicated>(a, s);
-    return launch_scalar<1, 128, kSelfBranch>(a, s);
+    if (c.self_mode == kSelfPredicated)
+      return c.mass ? launch_scalar<1, 128, kSelfPredicated, true>(a, s) : launch_scalar<1, 128, kSelfPredicated>(a, s);
+    return c.mass ? launch_scalar<1, 128, kSelfBranch, true>(a, s) : launch_scalar<1, 128, kSelfBranch>(a, s);
   }
-#define NB_WSTREAM(RR, WW) \
-  if (c.family == 3 && c.r == RR && c.block == 32 * WW) return launch_wstream<RR, WW>(a, c.sms, s);
-  NB_WSTREAM(2, 1)
-  NB_WSTREAM(4, 1)
-  NB_WSTREAM(6, 1)
-  NB_WSTREAM(8, 1)
-  NB_WSTREAM(2, 2)
-  NB_WSTREAM(4, 2)
-  NB_WSTREAM(4, 4)
-#undef NB_WSTREAM
   if (c.family == 4 && a.acc && a.progress && a.epoch) {  // j-segmented warp-streaming launch
     // (R, resident warps per SM promised to ptxas): the three tuned points, profiles/r01_tuning_log.txt
-    if (c.r == 2) return launch_wseg_mb<2, 28>(a, c.sms, a.progress, a.epoch, s);
-    if (c.r == 4) return launch_wseg_mb<4, 20>(a, c.sms, a.progress, a.epoch, s);
-    if (c.r == 6) return launch_wseg_mb<6, 14>(a, c.sms, a.progress, a.epoch, s);
+    if (c.r == 2) return c.mass ? launch_wseg_mb<2, 28, true>(a, c.sms, a.progress, a.epoch, s) : launch_wseg_mb<2, 28, false>(a, c.sms, a.progress, a.epoch, s);
+    if (c.r == 4) return c.mass ? launch_wseg_mb<4, 20, true>(a, c.sms, a.progress, a.epoch, s) : launch_wseg_mb<4, 20, false>(a, c.sms, a.progress, a.epoch, s);
+    if (c.r == 6) return c.mass ? launch_wseg_mb<6, 14, true>(a, c.sms, a.progress, a.epoch, s) : launch_wseg_mb<6, 14, false>(a, c.sms, a.progress, a.epoch, s);
   }
-  if (c.family == 4) {  // no hand-off buffers (caller-owned memory entry): plain warp-streaming
-    if (c.r == 2) return launch_wstream<2, 1>(a, c.sms, s);
-    if (c.r == 4) return launch_wstream<4, 1>(a, c.sms, s);
-    if (c.r == 6) return launch_wstream<6, 1>(a, c.sms, s);
+  if (c.family == 3 || c.family == 4) {  // unsegmented (also: caller-owned memory entry, no hand-off buffers)
+#define NB_WSTREAM(RR, WW)                                   \
+  if (c.r == RR && (c.block == 32 * WW || (c.family == 4 && WW == 1))) \
+    return c.mass ? launch_wstream<RR, WW, true>(a, c.sms, s) : launch_wstream<RR, WW, false>(a, c.sms, s);
+    NB_WSTREAM(2, 1)
+    NB_WSTREAM(4, 1)
+    NB_WSTREAM(6, 1)
+    NB_WSTREAM(8, 1)
+    NB_WSTREAM(4, 2)
+    NB_WSTREAM(4, 4)
+#undef NB_WSTREAM
   }
+  if (c.mass) return cudaErrorInvalidConfiguration;  // masses: AUTO / GENERIC kernels only
 #define NB_PACKED(RR, BB) \
   if (c.family == 1 && c.r == RR && c.block == BB) return launch_packed<RR, BB>(a, s);
 #define NB_SCALAR(RR, BB) \
   if (c.family == 2 && c.r == RR && c.block == BB) return launch_scalar<RR, BB, kSelfNone>(a, s);
   NB_PACKED(2, 64)
   NB_PACKED(2, 128)
-  NB_PACKED(4, 64)
   NB_PACKED(4, 128)
   NB_PACKED(4, 256)
-  NB_PACKED(8, 64)
-  NB_PACKED(8, 128)
   NB_SCALAR(2, 64)
   NB_SCALAR(2, 128)
-  NB_SCALAR(4, 64)
   NB_SCALAR(4, 128)
   NB_SCALAR(4, 256)
-  NB_SCALAR(8, 128)
 #undef NB_PACKED
 #undef NB_SCALAR
   return cudaErrorInvalidConfiguration;

@@ -54,6 +54,7 @@ struct KernelConfig {
   int block;   // threads per CTA
   int self_mode;
   int sms;     // SM count of the device the launch goes to (residency planning)
+  int mass;    // 1: multiply each term by the j-body's mass (float4.w); extension, SURVEY 8(f)-3
 };
 
 // true when the unpredicated kernels reproduce the BRANCH result bit-for-bit for this eps:
@@ -62,12 +63,14 @@ bool eps_allows_unpredicated(float eps);
 
 // picks the configuration for a shard of i_count bodies on a device with `sms` SMs
 KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uint32_t i_count,
-                           int sms);
+                           int sms, bool has_mass);
 const char *config_name(const KernelConfig &c, char *buf, size_t len);
 
 // asynchronous launch on `stream`; returns the CUDA error of the launch
 cudaError_t launch_step(const KernelConfig &c, const StepArgs &a, cudaStream_t stream);
 
+// overwrite float4.w (the mass slot) of `count` bodies from m[] (device) or with the constant w
+cudaError_t launch_set_w(float4 *pos, const float *m, float w, uint32_t count, cudaStream_t stream);
 // float4 AoS -> three SoA arrays (read-back for the reference's ParticleData layout)
 cudaError_t launch_deinterleave(const float4 *src, float *x, float *y, float *z, uint32_t count,
                                 cudaStream_t stream);

@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "nbody_destroy", "nbody_set_kernel", "nbody_kernel_name", "nbody_set_state", "nbody_set_mass",
     "nbody_step", "nbody_last_step_ms", "nbody_last_step_device_ms", "nbody_launch_count",
     "nbody_read_pos", "nbody_read_vel", "nbody_read_pos_f4", "nbody_read_vel_f4",
+    "nbody_save_state", "nbody_load_state",
     "nbody_device_name", "nbody_num_particles", "nbody_num_gpus", "nbody_world_size",
     "nbody_compute_accel", "nbody_launch_step_device",
 ]
@@ -116,6 +117,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.nbody_read_vel.argtypes = [H] + [_fp] * 3
     lib.nbody_read_pos_f4.argtypes = [H, _fp]
     lib.nbody_read_vel_f4.argtypes = [H, _fp]
+    lib.nbody_save_state.argtypes = [H, ctypes.c_char_p]
+    lib.nbody_load_state.argtypes = [H, ctypes.c_char_p]
     lib.nbody_device_name.argtypes = [H]
     lib.nbody_device_name.restype = ctypes.c_char_p
     lib.nbody_num_particles.argtypes = [H]
@@ -234,6 +237,23 @@ class DiskGalaxySimulator:
         arrs = [np.ascontiguousarray(a, np.float32) for a in (x, y, z, vx, vy, vz)]
         assert all(a.shape == (self.params.numParticles,) for a in arrs)
         _check(self._lib, self._lib.nbody_set_state(self._h, *[_ptr(a) for a in arrs]), "nbody_set_state")
+        self._host_fresh = False
+
+    def setMass(self, m):
+        """per-body masses (float4.w); None restores the reference's unit masses"""
+        if m is None:
+            _check(self._lib, self._lib.nbody_set_mass(self._h, None), "nbody_set_mass")
+        else:
+            a = np.ascontiguousarray(m, np.float32)
+            assert a.shape == (self.params.numParticles,)
+            _check(self._lib, self._lib.nbody_set_mass(self._h, _ptr(a)), "nbody_set_mass")
+        self._host_fresh = False
+
+    def saveState(self, path: str):
+        _check(self._lib, self._lib.nbody_save_state(self._h, path.encode()), "nbody_save_state")
+
+    def loadState(self, path: str):
+        _check(self._lib, self._lib.nbody_load_state(self._h, path.encode()), "nbody_load_state")
         self._host_fresh = False
 
     def setKernel(self, kernel: int):

@@ -154,6 +154,16 @@ int nbody_read_vel(nbody_handle *h, float *vx, float *vy, float *vz);
 int nbody_read_pos_f4(nbody_handle *h, float *xyzw);
 int nbody_read_vel_f4(nbody_handle *h, float *xyzw);
 
+/*
+ * Checkpoint / resume (the reference has none).  Little-endian binary file:
+ *   char magic[8] = "NBB200\0\1"; uint64 n; float G, dt, damping, dist_eps; int32 iters_per_frame,
+ *   calc_method, has_mass, reserved;  then float32[n] x, y, z, vx, vy, vz (and m when has_mass).
+ * Loading restores positions, velocities and masses into a handle created for the same n (the
+ * handle's own SimParam stays in force); stepping then continues bit-identically.
+ */
+int nbody_save_state(nbody_handle *h, const char *path);
+int nbody_load_state(nbody_handle *h, const char *path);
+
 /* replaces DiskGalaxySimulator::getDeviceName (src/simulator.cu:36-45) */
 const char *nbody_device_name(nbody_handle *h);
 uint64_t    nbody_num_particles(nbody_handle *h);

@@ -217,6 +217,40 @@ int oracle_accel(uint64_t n, const float *x, const float *y, const float *z, flo
   return 0;
 }
 
+/* Extension (no reference counterpart: the reference is unit-mass, src/simulator.cu:204):
+ * per-body masses.  Each term's weight is w*m_j, one FP32 multiply after the rsqrt, then the same
+ * fma(r, w*m_j, a) accumulate -- the op order of the CUDA kernels' MASS variants.  BRANCH semantics. */
+int oracle_accel_mass(uint64_t n, const float *x, const float *y, const float *z, const float *m, float eps,
+                      uint64_t i_begin, uint64_t i_end, float *ax, float *ay, float *az) {
+  if (i_end > n || i_begin > i_end) return 1;
+#pragma omp parallel
+  {
+    unsigned csr = set_ftz();
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t i = (int64_t)i_begin; i < (int64_t)i_end; i++) {
+      float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+      const float px = -x[i], py = -y[i], pz = -z[i];
+      for (uint64_t j = 0; j < n; j++) {
+        if ((int64_t)j == i) continue;
+        float rx = x[j] + px, ry = y[j] + py, rz = z[j] + pz;
+        float t = ry * ry;
+        t = fmaf(rx, rx, t);
+        t = fmaf(rz, rz, t);
+        float d = t + eps;
+        float c = d * d;
+        c = d * c;
+        float w = (1.0f / sqrtf(c)) * m[j];
+        fx = fmaf(rx, w, fx);
+        fy = fmaf(ry, w, fy);
+        fz = fmaf(rz, w, fz);
+      }
+      ax[i - (int64_t)i_begin] = fx; ay[i - (int64_t)i_begin] = fy; az[i - (int64_t)i_begin] = fz;
+    }
+    restore_csr(csr);
+  }
+  return 0;
+}
+
 /* FP64 truth for the same sum (self term skipped), for error-budget reporting only */
 int oracle_accel_f64(uint64_t n, const float *x, const float *y, const float *z, float eps,
                      uint64_t i_begin, uint64_t i_end, double *ax, double *ay, double *az) {

