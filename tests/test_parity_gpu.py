@@ -414,3 +414,50 @@ def test_checkpoint_resume_is_bit_identical(nb, tmp_path):
         c.loadState(path)
     b.close()
     c.close()
+
+
+@pytest.mark.parametrize("n", [200001, 400003])
+def test_register_blocking_switch_points_ragged(nb, ref, n):
+    """sizes just past the R = 2 -> 4 -> 6 switch points, not a multiple of anything: exercises the
+    ragged last group of the R = 4 / R = 6 segmented kernels against the reference kernel"""
+    fx, fy, fz, _ = ref.reference_forces(n)
+    sim = _mk(nb, n)
+    assert ("_r4_" if n < 399000 else "_r6_") in sim.kernelName()
+    _assert_bits(sim.computeAccel(), [fx, fy, fz], f"forces N={n}")
+    sim.close()
+
+
+@pytest.mark.parametrize("segs", ["1", "3", "7", "64"])
+def test_segment_count_does_not_change_a_bit(nb, golden_dir, segs, monkeypatch):
+    """the j-segmented hand-off keeps one FP32 chain per body whatever the number of segments"""
+    monkeypatch.setenv("NBODY_SEGS", segs)
+    meta = json.load(open(os.path.join(golden_dir, "golden_meta.json")))
+    import oracle_lib
+    o = oracle_lib.Oracle()
+    sim = _mk(nb, 262144)
+    assert o.fnv1a64(sim.computeAccel()) == meta["force"]["262144"]["fnv1a64"]
+    sim.close()
+    sim = _mk(nb, 25600, simIterationsPerFrame=10)
+    sim.stepSim()
+    assert o.fnv1a64(_state(sim)) == meta["step10"]["25600"]["fnv1a64"]
+    sim.close()
+
+
+def test_two_handles_interleaved(nb):
+    """two simulators alive in one process, stepped alternately (per-device launch-plan caches,
+    per-handle hand-off epochs)"""
+    a = _mk(nb, 30000, simIterationsPerFrame=2)
+    b = _mk(nb, 50000, simIterationsPerFrame=3)
+    ra = _mk(nb, 30000, simIterationsPerFrame=4)
+    for _ in range(2):
+        a.stepSim()
+        b.stepSim()
+    ra.stepSim()
+    _assert_bits(_state(a), _state(ra), "interleaved handle")
+    for s in (a, b, ra):
+        s.close()
+
+
+def test_bad_gpu_count_is_rejected(nb):
+    with pytest.raises(nb.NBodyError, match="not present"):
+        nb.DiskGalaxySimulator(nb.SimParam(numParticles=1024), n_gpus=nb.device_count() + 1)
