@@ -178,7 +178,10 @@ def cpu_baseline(n_bodies: int, target_s: float = 12.0):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
     o = oracle_lib.Oracle()
     st = o.disk_galaxy(n_bodies)
-    probe = 256
+    # two-stage calibration (thread start-up dominates a tiny probe), then ~target_s of work
+    probe = 16 * o.num_threads()
+    o.time_accel(st[0], st[1], st[2], 1.0e-7, 0, probe, 1)
+    probe = max(probe, 4096)
     t = o.time_accel(st[0], st[1], st[2], 1.0e-7, 0, probe, 1)
     rate = probe * n_bodies / t
     i_sample = int(min(n_bodies, max(probe, (rate * target_s / n_bodies) // 16 * 16)))
@@ -200,10 +203,12 @@ def run_reference_arm(args, dist, emit):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
     o = oracle_lib.Oracle()
     st = o.disk_galaxy(n)
-    # bounded sample per step: ~3 s of CPU work
-    probe = 256
+    # bounded sample per step: ~3 s of CPU work (two-stage calibration: thread start-up dominates a tiny probe)
+    probe = 16 * o.num_threads()
+    o.time_accel(st[0], st[1], st[2], 1.0e-7, 0, probe, 1)
+    probe = min(n, max(probe, 2048))
     t = o.time_accel(st[0], st[1], st[2], 1.0e-7, 0, probe, 1)
-    i_sample = int(min(n, max(probe, (probe * n / t * 3.0 / n) // 16 * 16)))
+    i_sample = int(min(n, max(16, (probe / t * 3.0) // 16 * 16)))
     for _ in range(args.warmup):
         o.time_accel(st[0], st[1], st[2], 1.0e-7, 0, i_sample, 1)
     t0 = time.perf_counter()

@@ -361,6 +361,10 @@ int setup_exchange(nbody_handle *h) {
   const bool rank_mode = h->devs.size() == 1 && h->world > 1;
   h->exchange = 0;
   if (want_nccl || (!single_process && !rank_mode)) return 0;
+  if (h->world - 1 > nbody::kMaxPeers) {  // StepArgs carries at most kMaxPeers peer replicas
+    if (want_p2p) return fail(NBODY_E_INVALID, "NBODY_EXCHANGE=p2p supports at most %d GPUs", nbody::kMaxPeers + 1);
+    return 0;
+  }
 
   if (single_process) {
     for (auto &d : h->devs)

@@ -722,9 +722,18 @@ template <int R, int MINB, bool MASS>
 static cudaError_t launch_wseg_mb(const StepArgs &a, int sms, unsigned int *progress, unsigned int *epoch,
                                   cudaStream_t s) {
   const uint32_t groups = (a.i_count + 32 * R - 1) / (32 * R);
-  int k_max = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k_max, (const void *)force_wseg_kernel<R, MINB, MASS>, 32, 0);
+  static int k_max_cache[64] = {0};  // per device: resident CTAs per SM of this instantiation
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (k_max_cache[dev] == 0) {
+    int k = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, (const void *)force_wseg_kernel<R, MINB, MASS>, 32, 0);
+    if (e != cudaSuccess) return e;
+    k_max_cache[dev] = k > 0 ? k : 1;
+  }
+  const int k_max = k_max_cache[dev];
   const uint32_t nj = a.j_end - a.j_begin;
   uint32_t segs = plan_segments(groups, nj, sms, k_max);
   uint32_t seg_len = ((nj + segs - 1) / segs + 31u) / 32u * 32u;
