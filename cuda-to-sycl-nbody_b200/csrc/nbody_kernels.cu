@@ -391,6 +391,156 @@ __global__ void __launch_bounds__(32, MINB) force_wseg_kernel(const StepArgs a, 
 }
 
 // =============================================================================================
+// TMA-staged variant of the production kernel (comparison only, NBODY_KERNEL_CONFIG="6,32,5").
+// Same arithmetic and j-segmented hand-off; the warp's 32-body tiles are fetched by one lane with
+// cp.async.bulk (SASS: UBLKCP) into a 4-stage shared-memory ring, completion tracked by one
+// mbarrier per stage.  north_star: "TMA bulk copies where ncu shows they help" -- measured, they
+// do not: the loop is FMA-pipe bound with long_scoreboard ~ 0, see profiles/r01_tuning_log.txt.
+// =============================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int R, int MINB>
+__global__ void __launch_bounds__(32, MINB) force_wseg_tma_kernel(const StepArgs a, const uint32_t groups,
+                                                            const uint32_t segs, const uint32_t seg_len,
+                                                            unsigned int *progress, const unsigned int epoch) {
+  static_assert(R % 2 == 0, "packed kernel pairs i-bodies");
+  constexpr int NP = R / 2;
+  constexpr int TJ = 32;
+  constexpr int STAGES = 4;
+  __shared__ __align__(128) float4 s_tile[STAGES][TJ];
+  __shared__ __align__(8) unsigned long long s_bar[STAGES];
+  const int lane = threadIdx.x & 31;
+  const uint32_t seg = blockIdx.x / groups;
+  const uint32_t g = blockIdx.x - seg * groups;
+  const uint32_t warp_i = g * (uint32_t)(32 * R);
+  if (warp_i >= a.i_count) return;
+  const uint32_t j_begin = a.j_begin + seg * seg_len;
+  const uint32_t j_end = min(a.j_end, j_begin + seg_len);
+  const int flags = (seg == 0 ? (a.flags & kFirstChunk) : 0) | (seg == segs - 1 ? (a.flags & (kLastChunk | kAccelOut)) : 0);
+  const uint32_t nj = j_end - j_begin;
+  const uint32_t ntiles = (nj + TJ - 1) / TJ;
+
+  auto issue = [&](uint32_t t) {  // lane 0 only: arm the stage's barrier and start the bulk copy of tile t
+    const int st = t % STAGES;
+    const uint32_t bytes = min((uint32_t)TJ, nj - t * TJ) * 16u;
+    const uint32_t bar = smem_u32(&s_bar[st]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(&s_tile[st][0])),
+                 "l"(a.pos + j_begin + t * TJ), "r"(bytes), "r"(bar)
+                 : "memory");
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < STAGES; st++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[st])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (uint32_t t = 0; t < STAGES && t < ntiles; t++) issue(t);
+  }
+  __syncwarp();
+
+  u64 nx[NP], ny[NP], nz[NP], ax[NP], ay[NP], az[NP];
+  float4 own[R];
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    uint32_t li = warp_i + k * 32 + lane;
+    uint32_t lc = li < a.i_count ? li : a.i_count - 1;
+    own[k] = a.pos[a.i_begin + lc];
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    nx[p] = pack2(-own[2 * p].x, -own[2 * p + 1].x);
+    ny[p] = pack2(-own[2 * p].y, -own[2 * p + 1].y);
+    nz[p] = pack2(-own[2 * p].z, -own[2 * p + 1].z);
+  }
+  if (seg > 0) {
+    if (lane == 0) {
+      volatile unsigned int *p = progress + g;
+      while (*p != epoch + seg) {
+      }
+      __threadfence();
+    }
+    __syncwarp();
+  }
+  if (flags & kFirstChunk) {
+#pragma unroll
+    for (int p = 0; p < NP; p++) ax[p] = ay[p] = az[p] = 0ull;
+  } else {
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      float4 c[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        uint32_t li = warp_i + (2 * p + h) * 32 + lane;
+        uint32_t lc = li < a.i_count ? li : a.i_count - 1;
+        c[h] = __ldcg(&a.acc[lc]);
+      }
+      ax[p] = pack2(c[0].x, c[1].x);
+      ay[p] = pack2(c[0].y, c[1].y);
+      az[p] = pack2(c[0].z, c[1].z);
+    }
+  }
+  const u64 eps2 = pack2(a.eps, a.eps);
+  auto interact = [&](int st, int j) {
+    const float4 q = s_tile[st][j];
+    const u64 qx = pack2(q.x, q.x), qy = pack2(q.y, q.y), qz = pack2(q.z, q.z);
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      u64 rx = fadd2(qx, nx[p]);
+      u64 ry = fadd2(qy, ny[p]);
+      u64 rz = fadd2(qz, nz[p]);
+      u64 t = fmul2(ry, ry);
+      t = ffma2(rx, rx, t);
+      t = ffma2(rz, rz, t);
+      u64 d = fadd2(t, eps2);
+      u64 c = fmul2(d, d);
+      c = fmul2(d, c);
+      float c0, c1;
+      unpack2(c, c0, c1);
+      u64 w = pack2(frsq(c0), frsq(c1));
+      ax[p] = ffma2(rx, w, ax[p]);
+      ay[p] = ffma2(ry, w, ay[p]);
+      az[p] = ffma2(rz, w, az[p]);
+    }
+  };
+  for (uint32_t t = 0; t < ntiles; t++) {
+    const int st = t % STAGES;
+    const uint32_t parity = (t / STAGES) & 1u;
+    const uint32_t bar = smem_u32(&s_bar[st]);
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done)
+                   : "r"(bar), "r"(parity)
+                   : "memory");
+    const uint32_t cnt = min((uint32_t)TJ, nj - t * TJ);
+    if (cnt == TJ) {
+#pragma unroll
+      for (int j = 0; j < TJ; j++) interact(st, j);
+    } else {
+      for (uint32_t j = 0; j < cnt; j++) interact(st, (int)j);
+    }
+    __syncwarp();  // every lane is done reading the stage before it is refilled
+    if (lane == 0 && t + STAGES < ntiles) issue(t + STAGES);
+  }
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    const uint32_t li = warp_i + k * 32 + lane;
+    if (li >= a.i_count) continue;
+    float fx0, fx1, fy0, fy1, fz0, fz1;
+    unpack2(ax[k / 2], fx0, fx1);
+    unpack2(ay[k / 2], fy0, fy1);
+    unpack2(az[k / 2], fz0, fz1);
+    const float fx = (k & 1) ? fx1 : fx0, fy = (k & 1) ? fy1 : fy0, fz = (k & 1) ? fz1 : fz0;
+    finish_body(a, flags, li, fx, fy, fz, own[k]);
+  }
+  if (seg + 1 < segs) {
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(progress + g, epoch + seg + 1);
+  }
+}
+
+// =============================================================================================
 // scalar kernel: R i-bodies per thread, scalar FADD/FMUL/FFMA; also the generic/faithful path
 // (BRANCH predicate for any eps, PREDICATED as shipped)
 // =============================================================================================
@@ -587,7 +737,7 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
     if (got >= 2 && er > 0 && eb > 0) {
       r = er;
       block = eb;
-      if (got == 3 && ef >= 1 && ef <= 4) family = ef;
+      if (got == 3 && ef >= 1 && ef <= 5) family = ef;
     }
   }
   c = {family, r, block, kSelfNone, sms, has_mass ? 1 : 0};
@@ -595,7 +745,7 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
 }
 
 const char *config_name(const KernelConfig &c, char *buf, size_t len) {
-  const char *fam = c.family == 1 ? "packed_f32x2" : (c.family == 2 ? "scalar_blocked" : (c.family == 3 ? "wstream_f32x2" : (c.family == 4 ? "wseg_f32x2" : "generic")));
+  const char *fam = c.family == 1 ? "packed_f32x2" : (c.family == 2 ? "scalar_blocked" : (c.family == 3 ? "wstream_f32x2" : (c.family == 4 ? "wseg_f32x2" : (c.family == 5 ? "wseg_tma_f32x2" : "generic"))));
   const char *self = c.self_mode == kSelfNone ? "nopred"
                                               : (c.self_mode == kSelfBranch ? "branch" : "predicated");
   snprintf(buf, len, "%s_r%d_b%d_%s%s", fam, c.r, c.block, self, c.mass ? "_mass" : "");
@@ -745,12 +895,32 @@ static cudaError_t launch_wseg_mb(const StepArgs &a, int sms, unsigned int *prog
   return cudaGetLastError();
 }
 
+template <int R, int MINB>
+static cudaError_t launch_wseg_tma(const StepArgs &a, int sms, unsigned int *progress, unsigned int *epoch,
+                                   cudaStream_t s) {
+  const uint32_t groups = (a.i_count + 32 * R - 1) / (32 * R);
+  const uint32_t nj = a.j_end - a.j_begin;
+  uint32_t segs = plan_segments(groups, nj, sms, MINB);
+  uint32_t seg_len = ((nj + segs - 1) / segs + 31u) / 32u * 32u;
+  segs = (nj + seg_len - 1) / seg_len;
+  if (*epoch > 0xf0000000u) return cudaErrorInvalidValue;
+  const unsigned int ep = *epoch;
+  *epoch += segs;
+  force_wseg_tma_kernel<R, MINB><<<groups * segs, 32, 0, s>>>(a, groups, segs, seg_len, progress, ep);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_step(const KernelConfig &c, const StepArgs &a, cudaStream_t s) {
   if (a.i_count == 0) return cudaSuccess;
   if (c.family == 0) {
     if (c.self_mode == kSelfPredicated)
       return c.mass ? launch_scalar<1, 128, kSelfPredicated, true>(a, s) : launch_scalar<1, 128, kSelfPredicated>(a, s);
     return c.mass ? launch_scalar<1, 128, kSelfBranch, true>(a, s) : launch_scalar<1, 128, kSelfBranch>(a, s);
+  }
+  if (c.family == 5 && a.acc && a.progress && a.epoch && !c.mass) {  // TMA-staged comparison variant
+    if (c.r == 6) return launch_wseg_tma<6, 14>(a, c.sms, a.progress, a.epoch, s);
+    if (c.r == 4) return launch_wseg_tma<4, 20>(a, c.sms, a.progress, a.epoch, s);
+    return cudaErrorInvalidConfiguration;
   }
   if (c.family == 4 && a.acc && a.progress && a.epoch) {  // j-segmented warp-streaming launch
     // (R, resident warps per SM promised to ptxas): the three tuned points, profiles/r01_tuning_log.txt

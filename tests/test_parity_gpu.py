@@ -461,3 +461,18 @@ def test_two_handles_interleaved(nb):
 def test_bad_gpu_count_is_rejected(nb):
     with pytest.raises(nb.NBodyError, match="not present"):
         nb.DiskGalaxySimulator(nb.SimParam(numParticles=1024), n_gpus=nb.device_count() + 1)
+
+
+@pytest.mark.parametrize("cfg", ["6,32,5", "4,32,5", "4,32,3", "4,256,1"])
+def test_comparison_variants_stay_bit_exact(nb, golden_dir, cfg, monkeypatch):
+    """the kept comparison kernels (TMA/cp.async.bulk-staged, unsegmented warp-streaming, CTA-tiled)
+    compute the same bits as the production kernel and the reference"""
+    monkeypatch.setenv("NBODY_KERNEL_CONFIG", cfg)
+    meta = json.load(open(os.path.join(golden_dir, "golden_meta.json")))
+    import oracle_lib
+    o = oracle_lib.Oracle()
+    sim = _mk(nb, 262144)
+    if cfg.endswith(",1"):
+        sim.setKernel(nb.KERNEL_PACKED)
+    assert o.fnv1a64(sim.computeAccel()) == meta["force"]["262144"]["fnv1a64"], sim.kernelName()
+    sim.close()
