@@ -177,6 +177,7 @@ def cpu_baseline(n_bodies: int, target_s: float = 12.0):
     if not os.path.exists(oracle_lib.ORACLE_LIB):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
     o = oracle_lib.Oracle()
+    o.set_num_threads(len(os.sched_getaffinity(0)))
     st = o.disk_galaxy(n_bodies)
     # two-stage calibration (thread start-up dominates a tiny probe), then ~target_s of work
     probe = 16 * o.num_threads()
@@ -202,6 +203,7 @@ def run_reference_arm(args, dist, emit):
     if not os.path.exists(oracle_lib.ORACLE_LIB):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
     o = oracle_lib.Oracle()
+    o.set_num_threads(len(os.sched_getaffinity(0)))  # torchrun exports OMP_NUM_THREADS=1: use every core we may
     st = o.disk_galaxy(n)
     # bounded sample per step: ~3 s of CPU work (two-stage calibration: thread start-up dominates a tiny probe)
     probe = 16 * o.num_threads()

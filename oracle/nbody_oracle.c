@@ -320,6 +320,15 @@ double oracle_time_accel(uint64_t n, const float *x, const float *y, const float
   return best;
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the CPU-baseline legs ask for all cores */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

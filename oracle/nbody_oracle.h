@@ -22,6 +22,7 @@ int oracle_step(uint64_t n, float *x, float *y, float *z, float *vx, float *vy, 
 double   oracle_time_accel(uint64_t n, const float *x, const float *y, const float *z, float eps,
                            uint64_t i_begin, uint64_t i_count, int reps);
 int      oracle_num_threads(void);
+void     oracle_set_num_threads(int n);
 uint64_t oracle_fnv1a64(uint64_t n, int k, const float *const *arr);
 uint64_t oracle_fnv1a64_state(uint64_t n, const float *x, const float *y, const float *z,
                               const float *vx, const float *vy, const float *vz);

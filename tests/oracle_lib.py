@@ -74,6 +74,9 @@ class Oracle:
     def time_accel(self, x, y, z, eps, i_begin, i_count, reps=1):
         return float(self.L.oracle_time_accel(len(x), _p(x), _p(y), _p(z), eps, i_begin, i_count, reps))
 
+    def set_num_threads(self, n: int):
+        self.L.oracle_set_num_threads(int(n))
+
     def num_threads(self):
         return int(self.L.oracle_num_threads())
 
