@@ -862,6 +862,7 @@ static uint32_t plan_segments(uint32_t groups, uint32_t nj, int sms, int k_max) 
     if (v >= 1 && v <= 1024) return (uint32_t)v;
   }
   const double gens = (double)groups / ((double)sms * k_max);
+  if (gens < 0.25) return 1;  // far fewer warps than slots: later segments would only spin (measured, N < 64K)
   int segs = (int)ceil(16.0 / (gens > 0.05 ? gens : 0.05));
   if (segs > 64) segs = 64;
   while (segs > 1 && nj / segs < 4096) segs--;  // keep segments long: hand-off cost stays invisible
