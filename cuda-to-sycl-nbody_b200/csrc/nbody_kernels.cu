@@ -14,15 +14,20 @@
 // order -- spelled in PTX with explicit .rn.ftz so ptxas cannot re-contract it -- and is
 // bit-identical to the reference; the speed comes from how the sequence is fed and issued:
 //
-//   * j-bodies are staged through shared memory in CTA-wide tiles (double buffered, one
-//     __syncthreads per tile) and read with warp-uniform (broadcast) LDS;
+//   * the packed kernels pair two i-bodies in the two lanes of Blackwell's f32x2 instructions
+//     (FADD2 / FMUL2 / FFMA2): 12 FP32 instructions serve TWO interactions; the j-body is a
+//     scalar operand broadcast to both lanes by the instruction itself (SASS operand form
+//     `R.F32`), so the tile stays in its HBM float4 layout and costs one LDS.128 per j;
 //   * each thread register-blocks R i-bodies, so one LDS feeds R interactions;
-//   * the packed kernel pairs two i-bodies in the two lanes of Blackwell's f32x2 instructions
-//     (FADD2 / FMUL2 / FFMA2): 12 FP32 instructions serve TWO interactions, which takes the
-//     kernel off the issue-slot bound (13 slots/interaction) and onto the FMA-pipe bound;
-//     the j-body is a scalar operand broadcast to both lanes by the instruction itself
-//     (SASS operand form `R.F32`), so the tile stays in its HBM layout and costs one LDS.128;
-//   * no warp shuffles, no atomics, no j-split: the accumulate is a per-thread FMA chain.
+//   * production kernel (force_wseg_kernel): one warp per CTA, warp-private 32-body j-tiles
+//     (LDG.128 -> STS.128 -> __syncwarp -> broadcast LDS.128, double buffered, no CTA barrier),
+//     and the j-sweep of a body group cut into consecutive CTAs of one grid that hand the
+//     accumulators on through L2 in order -- still one FP32 chain per body, but short units,
+//     which removes the low-occupancy tail of the launch;
+//   * comparison kernels kept selectable: unsegmented warp-streaming, CTA-tiled packed (256-body
+//     tiles, one __syncthreads per tile), TMA (cp.async.bulk + mbarrier) staged, scalar FFMA;
+//   * no warp shuffles, no atomics, no j-split reduction: the accumulate is a per-thread FMA chain.
+// Measurements behind every choice: profiles/r01_tuning_log.txt, DESIGN.md section 5.
 #include "nbody_kernels.cuh"
 
 #include <math.h>

@@ -133,3 +133,20 @@ def test_headless_driver_and_reference_main_fail_fast_without_gpu(nb):
         pytest.skip("driver not built")
     r = subprocess.run([exe, "4", "1", "0.999", "0.001", "1e-3", "2.0", "3"], capture_output=True, text=True)
     assert r.returncode != 0 and "GPUassert:" in r.stderr
+
+
+def test_shard_plan_properties_hypothesis(nb):
+    """property test: shards tile [0, n) in rank order, 128-aligned except the ragged tail"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(n=st.integers(min_value=1, max_value=(1 << 31) - 1), world=st.integers(min_value=1, max_value=16))
+    def check(n, world):
+        pos = 0
+        for r in range(world):
+            b, c = nb.plan_shard(n, world, r)
+            assert b == pos and (c == 0 or b % 128 == 0)
+            pos += c
+        assert pos == n
+
+    check()
