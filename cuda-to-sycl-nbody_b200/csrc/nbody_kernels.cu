@@ -396,6 +396,90 @@ __global__ void __launch_bounds__(32, MINB) force_wseg_kernel(const StepArgs a, 
 }
 
 // =============================================================================================
+// small-N kernel: one warp per CTA, warp-private tiles like the production kernel, but SCALAR
+// FP32 ops and R i-bodies per lane (R = 1 or 2).  With N of a few ten thousand bodies there are
+// fewer warps than SM sub-partitions can hold, so lanes, not issue slots, are scarce: one body per
+// lane doubles the number of warps relative to the packed R = 2 kernel, and a scalar op issues in
+// one cycle where a packed one holds the pipe for two.  Same op sequence, bit-exact.
+// =============================================================================================
+template <int R>
+__global__ void __launch_bounds__(32) force_wsmall_kernel(const StepArgs a) {
+  constexpr int TJ = 32;
+  __shared__ __align__(16) float4 tile[2][TJ];
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp_i = blockIdx.x * (uint32_t)(32 * R);
+  if (warp_i >= a.i_count) return;
+  float nx[R], ny[R], nz[R], ax[R], ay[R], az[R];
+  float4 own[R];
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    uint32_t li = warp_i + k * 32 + lane;
+    uint32_t lc = li < a.i_count ? li : a.i_count - 1;
+    own[k] = a.pos[a.i_begin + lc];
+    nx[k] = -own[k].x;
+    ny[k] = -own[k].y;
+    nz[k] = -own[k].z;
+    if (a.flags & kFirstChunk) {
+      ax[k] = ay[k] = az[k] = 0.0f;
+    } else {
+      float4 c = __ldcg(&a.acc[lc]);
+      ax[k] = c.x;
+      ay[k] = c.y;
+      az[k] = c.z;
+    }
+  }
+  const float eps = a.eps;
+  const uint32_t nj = a.j_end - a.j_begin;
+  const uint32_t ntiles = (nj + TJ - 1) / TJ;
+  auto fetch = [&](uint32_t t) -> float4 {
+    uint32_t j = a.j_begin + t * TJ + lane;
+    return a.pos[j < a.j_end ? j : a.j_end - 1];
+  };
+  auto interact = [&](int buf, int j) {
+    const float4 q = tile[buf][j];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      float rx = fadd(q.x, nx[k]);
+      float ry = fadd(q.y, ny[k]);
+      float rz = fadd(q.z, nz[k]);
+      float t = fmul(ry, ry);
+      t = ffma(rx, rx, t);
+      t = ffma(rz, rz, t);
+      float d = fadd(t, eps);
+      float c = fmul(d, d);
+      c = fmul(d, c);
+      float w = frsq(c);
+      ax[k] = ffma(rx, w, ax[k]);
+      ay[k] = ffma(ry, w, ay[k]);
+      az[k] = ffma(rz, w, az[k]);
+    }
+  };
+  if (ntiles > 0) tile[0][lane] = fetch(0);
+  __syncwarp();
+  for (uint32_t t = 0; t < ntiles; t++) {
+    const int buf = t & 1;
+    float4 nxt;
+    const bool more = t + 1 < ntiles;
+    if (more) nxt = fetch(t + 1);
+    const uint32_t cnt = min((uint32_t)TJ, nj - t * TJ);
+    if (cnt == TJ) {
+#pragma unroll
+      for (int j = 0; j < TJ; j++) interact(buf, j);
+    } else {
+      for (uint32_t j = 0; j < cnt; j++) interact(buf, (int)j);
+    }
+    if (more) tile[buf ^ 1][lane] = nxt;
+    __syncwarp();
+  }
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    const uint32_t li = warp_i + k * 32 + lane;
+    if (li >= a.i_count) continue;
+    finish_body(a, a.flags, li, ax[k], ay[k], az[k], own[k]);
+  }
+}
+
+// =============================================================================================
 // TMA-staged variant of the production kernel (comparison only, NBODY_KERNEL_CONFIG="6,32,5").
 // Same arithmetic and j-segmented hand-off; the warp's 32-body tiles are fetched by one lane with
 // cp.async.bulk (SASS: UBLKCP) into a 4-stage shared-memory ring, completion tracked by one
@@ -715,7 +799,8 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
     c = {0, 1, 128, kSelfBranch, sms, has_mass ? 1 : 0};
     return c;
   }
-  // family: 4 = j-segmented warp-streaming packed (AUTO), 3 = unsegmented, 1 = CTA-tiled packed, 2 = CTA-tiled scalar
+  // family: 4 = j-segmented warp-streaming packed (AUTO), 6 = small-N scalar warp-streaming (AUTO, tiny shards),
+  // 3 = unsegmented, 5 = TMA-staged, 1 = CTA-tiled packed, 2 = CTA-tiled scalar
   int family = requested_kernel == 3 ? 2 : (requested_kernel == 2 ? 1 : 4);
   int r = 4, block = 128;
   if (family == 4) {
@@ -726,6 +811,12 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
     r = 6;
     if ((uint64_t)i_count < (uint64_t)sms * 2700u) r = 4;  // < ~400K bodies on 148 SMs
     if ((uint64_t)i_count < (uint64_t)sms * 1350u) r = 2;  // < ~200K bodies
+    if ((uint64_t)i_count <= (uint64_t)sms * 128u && !has_mass) {
+      // at most one warp per SM sub-partition even at one body per lane (the reference's interactive
+      // sizes, N <= ~19K): scalar ops, R = 1 -- 1.5x the packed kernel there (tools/small_n.py)
+      family = 6;
+      r = 1;
+    }
   } else if (family == 3) {
     block = 32;
     if ((uint64_t)i_count < (uint64_t)sms * 20u * 128u) r = 2;
@@ -742,7 +833,7 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
     if (got >= 2 && er > 0 && eb > 0) {
       r = er;
       block = eb;
-      if (got == 3 && ef >= 1 && ef <= 5) family = ef;
+      if (got == 3 && ef >= 1 && ef <= 6) family = ef;
     }
   }
   c = {family, r, block, kSelfNone, sms, has_mass ? 1 : 0};
@@ -750,7 +841,7 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
 }
 
 const char *config_name(const KernelConfig &c, char *buf, size_t len) {
-  const char *fam = c.family == 1 ? "packed_f32x2" : (c.family == 2 ? "scalar_blocked" : (c.family == 3 ? "wstream_f32x2" : (c.family == 4 ? "wseg_f32x2" : (c.family == 5 ? "wseg_tma_f32x2" : "generic"))));
+  const char *fam = c.family == 1 ? "packed_f32x2" : (c.family == 2 ? "scalar_blocked" : (c.family == 3 ? "wstream_f32x2" : (c.family == 4 ? "wseg_f32x2" : (c.family == 5 ? "wseg_tma_f32x2" : (c.family == 6 ? "wsmall_scalar" : "generic")))));
   const char *self = c.self_mode == kSelfNone ? "nopred"
                                               : (c.self_mode == kSelfBranch ? "branch" : "predicated");
   snprintf(buf, len, "%s_r%d_b%d_%s%s", fam, c.r, c.block, self, c.mass ? "_mass" : "");
@@ -922,6 +1013,14 @@ cudaError_t launch_step(const KernelConfig &c, const StepArgs &a, cudaStream_t s
     if (c.self_mode == kSelfPredicated)
       return c.mass ? launch_scalar<1, 128, kSelfPredicated, true>(a, s) : launch_scalar<1, 128, kSelfPredicated>(a, s);
     return c.mass ? launch_scalar<1, 128, kSelfBranch, true>(a, s) : launch_scalar<1, 128, kSelfBranch>(a, s);
+  }
+  if (c.family == 6 && !c.mass) {  // small-N scalar warp-streaming kernel
+    const uint32_t per = 32u * (uint32_t)c.r;
+    const uint32_t ctas = (a.i_count + per - 1) / per;
+    if (c.r == 1) force_wsmall_kernel<1><<<ctas, 32, 0, s>>>(a);
+    else if (c.r == 2) force_wsmall_kernel<2><<<ctas, 32, 0, s>>>(a);
+    else return cudaErrorInvalidConfiguration;
+    return cudaGetLastError();
   }
   if (c.family == 5 && a.acc && a.progress && a.epoch && !c.mass) {  // TMA-staged comparison variant
     if (c.r == 6) return launch_wseg_tma<6, 14>(a, c.sms, a.progress, a.epoch, s);

@@ -49,7 +49,8 @@ enum SelfMode : int {
 struct KernelConfig {
   int family;  // 0 = generic scalar (R=1, predicated), 1 = CTA-tiled packed f32x2,
                // 2 = CTA-tiled scalar blocked, 3 = warp-streaming packed f32x2,
-               // 4 = warp-streaming packed f32x2 with j-segmented hand-off (production)
+               // 4 = warp-streaming packed f32x2 with j-segmented hand-off (production),
+               // 5 = TMA-staged comparison variant, 6 = small-N scalar warp-streaming
   int r;       // i-bodies per thread
   int block;   // threads per CTA
   int self_mode;
