@@ -3,7 +3,7 @@ import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "cuda-to-sycl-nbody_b200")); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import nbody_b200 as nb, refsim
-for n in (12800, 25600, 64000, 131072, 262144):
+for n in [int(v) for v in (sys.argv[1].split(',') if len(sys.argv) > 1 else '12800,25600,64000,131072'.split(','))]:
     iters = 64
     ref = refsim.RefSimulator(n, iters=1)
     best_ref = 1e9
