@@ -353,6 +353,20 @@ __global__ void __launch_bounds__(32 * WARPS, 28 / WARPS) force_wstream_kernel(c
   wstream_body<R, MASS>(a, a.j_begin, a.j_end, a.flags, warp_i, s_tile[warp], lane);
 }
 
+// Spin (with back-off) until the predecessor segment of this body group has published its
+// accumulators.  The predecessor CTA has a lower blockIdx and is therefore already resident or done;
+// legitimate waits are at most one unit long (<= a few seconds at the largest sizes).  Should the
+// dispatch-order assumption ever be violated, trap after ~20 s instead of hanging the device.
+__device__ __forceinline__ void wait_for_segment(unsigned int *word, unsigned int target) {
+  volatile unsigned int *p = word;
+  unsigned int spins = 0;
+  while (*p != target) {
+    __nanosleep(128);
+    if (++spins > (1u << 27)) __trap();
+  }
+  __threadfence();
+}
+
 // (28 resident warps per SM = a 72-register budget: the schedule ptxas finds there is the fastest
 // measured -- 60 or 79 registers lose 6-11 %, profiles/r01_tuning_log.txt)
 // j-segmented launch.  A body-group's sweep over j is cut into `segs` consecutive segments that
@@ -379,12 +393,7 @@ __global__ void __launch_bounds__(32, MINB) force_wseg_kernel(const StepArgs a, 
   const uint32_t j_end = min(a.j_end, j_begin + seg_len);
   const int flags = (seg == 0 ? (a.flags & kFirstChunk) : 0) | (seg == segs - 1 ? (a.flags & (kLastChunk | kAccelOut)) : 0);
   if (seg > 0) {
-    if (lane == 0) {
-      volatile unsigned int *p = progress + g;
-      while (*p != epoch + seg) {
-      }
-      __threadfence();
-    }
+    if (lane == 0) wait_for_segment(progress + g, epoch + seg);
     __syncwarp();
   }
   wstream_body<R, MASS>(a, j_begin, j_end, flags, warp_i, s_tile, lane);
@@ -542,12 +551,7 @@ __global__ void __launch_bounds__(32, MINB) force_wseg_tma_kernel(const StepArgs
     nz[p] = pack2(-own[2 * p].z, -own[2 * p + 1].z);
   }
   if (seg > 0) {
-    if (lane == 0) {
-      volatile unsigned int *p = progress + g;
-      while (*p != epoch + seg) {
-      }
-      __threadfence();
-    }
+    if (lane == 0) wait_for_segment(progress + g, epoch + seg);
     __syncwarp();
   }
   if (flags & kFirstChunk) {
