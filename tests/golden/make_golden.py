@@ -16,9 +16,19 @@ Fixtures
   step10_n2048.npz          pos+vel after 10 iterations with SimParam defaults, N=2048
   cloud_n1000.npz           a seeded uniform cloud (inputs included) and its reference forces, eps=1e-3
   predicated_n1024.npz      state after 1 step of the shipped PREDICATED kernel (zero force)
+  predicated_fixed_n1024.npz  state after 1 step of the README-intended PREDICATED kernel, i.e. the reference
+                            with src/simulator.cu:209 changed to (i != id) (oracle/Makefile: ref_fixed)
+  golden_meta.json["force_sha256"], ["step1_sha256"], ["force_fixed_sha256"]
+                            SHA-256 of the float32 byte stream (fx[i],fy[i],fz[i] interleaved per body; for
+                            step1: x,y,z,vx,vy,vz) at the BASELINE sizes 262144 / 1M / 4M / 16M -- what bench.py,
+                            smoke() and the full-size parity tests compare the CUDA path with
+
+    python tests/golden/make_golden.py            # everything (the 16M force pass alone is ~4 min of B200)
+    python tests/golden/make_golden.py --big-only # only the *_sha256 entries, merged into the committed meta
 """
 from __future__ import annotations
 
+import hashlib
 import json
 import os
 import subprocess
@@ -45,8 +55,59 @@ def fnv1a64(arrays) -> str:
     return f"{h:016x}"
 
 
+def sha256_f32(arrays) -> str:
+    """SHA-256 over the float32 bit patterns, interleaved per body (a0[i], a1[i], ...)."""
+    inter = np.stack([np.ascontiguousarray(a, np.float32) for a in arrays], axis=1).reshape(-1)
+    return hashlib.sha256(inter.tobytes()).hexdigest()
+
+
+BIG_FORCE = (262144, 400003, 1048576, 4194304, 16777216)
+BIG_STEP1 = (262144, 1048576)
+
+
+def big(meta):
+    """full-size pins: one launch of the reference kernel per size (1M: 0.9 s, 4M: 14 s, 16M: ~220 s on B200)"""
+    meta.setdefault("force_sha256", {})
+    meta.setdefault("step1_sha256", {})
+    meta.setdefault("force_fixed_sha256", {})
+    sizes = BIG_FORCE if "--no-16m" not in sys.argv else BIG_FORCE[:-1]
+    for n in sizes:
+        fx, fy, fz, _ = refsim.reference_forces(n)
+        meta["force_sha256"][str(n)] = sha256_f32([fx, fy, fz])
+        print("force_sha256", n, meta["force_sha256"][str(n)], flush=True)
+        with open(os.path.join(OUT, "golden_meta.json"), "w") as f:  # keep what is done if the lease ends early
+            json.dump(meta, f, indent=1)
+    for n in BIG_STEP1:
+        sim = refsim.RefSimulator(n, iters=1)
+        sim.step()
+        meta["step1_sha256"][str(n)] = sha256_f32(sim.state())
+        sim.close()
+        print("step1_sha256", n, meta["step1_sha256"][str(n)], flush=True)
+    if refsim.available("fixed"):
+        for n in (25600, 262144):
+            fx, fy, fz, _ = refsim.reference_forces(n, calc=1, lib="fixed")
+            meta["force_fixed_sha256"][str(n)] = sha256_f32([fx, fy, fz])
+            print("force_fixed_sha256", n, meta["force_fixed_sha256"][str(n)], flush=True)
+        n = 1024
+        sim = refsim.RefSimulator(n, iters=1, calc=1, lib="fixed")
+        sim.step()
+        s = sim.state()
+        sim.close()
+        np.savez(os.path.join(OUT, "predicated_fixed_n1024.npz"), x=s[0], y=s[1], z=s[2], vx=s[3], vy=s[4], vz=s[5])
+        fx, fy, fz, _ = refsim.reference_forces(2048, calc=1, lib="fixed")
+        np.savez(os.path.join(OUT, "force_fixed_n2048.npz"), fx=fx, fy=fy, fz=fz)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--big-only" in sys.argv:
+        with open(os.path.join(HERE, "golden_meta.json")) as f:
+            meta = json.load(f)
+        big(meta)
+        with open(os.path.join(OUT, "golden_meta.json"), "w") as f:
+            json.dump(meta, f, indent=1)
+        print("wrote", OUT)
+        return
     meta = {"provenance": {}, "init": {}, "force": {}, "step10": {}}
     try:
         meta["provenance"]["gpu"] = subprocess.run(
@@ -99,6 +160,7 @@ def main():
     sim.close()
     np.savez(os.path.join(OUT, "predicated_n1024.npz"), x=s[0], y=s[1], z=s[2], vx=s[3], vy=s[4], vz=s[5])
 
+    big(meta)
     with open(os.path.join(OUT, "golden_meta.json"), "w") as f:
         json.dump(meta, f, indent=1)
     print("wrote", OUT)

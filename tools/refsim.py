@@ -12,18 +12,19 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libnbody_ref.so")
+# the same reference with src/simulator.cu:209 changed to (i != id): oracle of PREDICATED_FIXED
+REF_FIXED_LIB = os.path.join(ROOT, "oracle", "_ref", "libnbody_ref_fixed.so")
 _fp = ctypes.POINTER(ctypes.c_float)
-_lib = None
+_libs = {}
 
 
-def available() -> bool:
-    return os.path.exists(REF_LIB)
+def available(which: str = "ref") -> bool:
+    return os.path.exists(REF_FIXED_LIB if which == "fixed" else REF_LIB)
 
 
-def load():
-    global _lib
-    if _lib is None:
-        lib = ctypes.CDLL(REF_LIB)
+def load(which: str = "ref"):
+    if which not in _libs:
+        lib = ctypes.CDLL(REF_FIXED_LIB if which == "fixed" else REF_LIB)
         lib.ref_create.restype = ctypes.c_void_p
         lib.ref_create.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_ulonglong, ctypes.c_int,
                                    ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int]
@@ -37,8 +38,8 @@ def load():
         lib.ref_device_name.restype = ctypes.c_char_p
         lib.ref_time_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         lib.ref_time_kernel.restype = ctypes.c_float
-        _lib = lib
-    return _lib
+        _libs[which] = lib
+    return _libs[which]
 
 
 def _p(a):
@@ -49,8 +50,8 @@ def _p(a):
 class RefSimulator:
     """The reference's DiskGalaxySimulator (src/simulator.cuh:129-160), driven through the shim."""
 
-    def __init__(self, n, G=2.0, dt=0.005, iters=4, damping=0.999998, eps=1.0e-7, gw=64, calc=0):
-        self.lib = load()
+    def __init__(self, n, G=2.0, dt=0.005, iters=4, damping=0.999998, eps=1.0e-7, gw=64, calc=0, lib="ref"):
+        self.lib = load(lib)
         self.n = n
         self.h = self.lib.ref_create(G, dt, n, iters, damping, eps, gw, calc)
 
@@ -87,10 +88,10 @@ class RefSimulator:
             pass
 
 
-def reference_forces(n, eps=1.0e-7, state=None, calc=0):
+def reference_forces(n, eps=1.0e-7, state=None, calc=0, lib="ref"):
     """Raw force sums of the reference kernel via the damping=0, dt=1, G=1 trick:
     v' = fma(F*1, 1, v*0) = F exactly.  Returns (fx, fy, fz, initial_state)."""
-    sim = RefSimulator(n, G=1.0, dt=1.0, iters=1, damping=0.0, eps=eps, calc=calc)
+    sim = RefSimulator(n, G=1.0, dt=1.0, iters=1, damping=0.0, eps=eps, calc=calc, lib=lib)
     if state is not None:
         sim.set_state(*state)
     init = sim.state()
