@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native all-pairs N-body step.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--bodies N]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--bodies N | --weak-base B]
 
 Metric (BASELINE.json): G body-interactions/s = steps * N^2 / seconds / 1e9 (self pair
 included), and its fraction of the FP32 roofline at 20 flop/interaction.
@@ -9,16 +9,26 @@ included), and its fraction of the FP32 roofline at 20 flop/interaction.
 Workload: the reference's default-seeded disk galaxy with SimParam defaults (G=2, dt=0.005,
 damping=0.999998, distEps=1e-7, BRANCH), one force+integrate iteration per "step".
   --gpus 1 : N = 1,048,576  (BASELINE configs[2]: 1xB200, 1M bodies)
-  --gpus>1 : N = 4,194,304  (BASELINE configs[3]: bodies sharded by i-range, NCCL position
-             exchange per step), strong scaling.  Launched by torchrun, one rank per GPU;
+  --gpus>1 : N = 4,194,304  (BASELINE configs[3]: bodies sharded by i-range, position exchange
+             per step), strong scaling.  Launched by torchrun, one rank per GPU;
              without torchrun env one process drives all N GPUs (the drop-in class's mode).
+  --bodies N         any other size (configs[4]: 16,777,216 strong scaling at 1/2/4/8 GPUs)
+  --weak-base B      weak scaling in WORK: N = B*sqrt(gpus) rounded to 256, so N^2/gpus is constant
+                     (B = 5931642 ends at 16,777,216 bodies on 8 GPUs)
+
+Parity: before anything is timed, one force pass of the (sharded) handle is hashed (SHA-256 of all 3N
+float32 force components) and compared with what the UNMODIFIED reference kernel produced for the same
+galaxy on a B200 (tests/golden/golden_meta.json: 262144, 400003, 1M, 4M, 16M).  A mismatch aborts the
+run; sizes without a committed golden report "matches_reference_golden": null.
 
 Timing: W >= 3 untimed warm-up steps, then K steps, each timed ON THE DEVICE by CUDA events
 on the library's compute stream (nbody_last_step_device_ms: first launch -> last kernel and
 position exchange of that step), L2 flushed between steps, barrier + device synchronise on
 both sides of the timed region, MAX over ranks.  `value` has the state resident in HBM;
 `e2e` is the same step driven through the C ABI with HOST buffers (nbody_set_state from
-pinned memory + nbody_step + nbody_read_pos/vel into pinned memory) timed by the host clock.
+pinned memory + nbody_step + read-back into pinned memory) timed by the host clock; with one rank
+per GPU every rank uploads all N positions (each GPU keeps a full replica) and reads back the bodies
+it owns (nbody_read_local), as a process-per-GPU application would.
 
 --impl reference: the reference's CPU implementation of this path cannot be built here (SYCL /
 OpenCL-CPU toolchain absent), so the arm times the oracle's C/OpenMP port of
@@ -27,7 +37,9 @@ src_sycl/simulator.dp.cpp:315-360 on all host threads, on a bounded sample of th
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -191,14 +203,44 @@ def cpu_baseline(n_bodies: int, target_s: float = 12.0):
     return {"value": g, "unit": METRIC, "cores": o.num_threads(), "kind": "port",
             "sample": f"forces of the first {i_sample} bodies against all {n_bodies} (1 pass, {t:.2f} s), "
                       f"C/OpenMP restatement of src_sycl/simulator.dp.cpp:315-360, not the SYCL binary",
-            "seconds": t, "host_cpus": os.cpu_count()}
+            "seconds": t, "host_cpus": os.cpu_count(), "cpu_model": cpu_model(),
+            "config0": cpu_config0(o)}
+
+
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_config0(o, frames: int = 3):
+    """BASELINE configs[0] as named: 25600 particles (100 x 256), 10 steps per frame, the whole frame
+    (force + integrate, all 10 iterations) timed by the host clock as src_sycl/simulator.dp.cpp:59-112
+    does; invocation README.md:71-75 (`run_nbody.sh -b dpcpp 100 10`).  Full frames, no sampling."""
+    n, iters = 25600, 10
+    st = o.disk_galaxy(n)
+    st = o.step(st, iters=1)  # warm-up (thread pool, page faults)
+    times = []
+    for _ in range(frames):
+        t0 = time.perf_counter()
+        st = o.step(st, iters=iters)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return {"workload": "N=25600 (100x256), simIterationsPerFrame=10, SimParam defaults, full frames",
+            "ms_per_frame": best * 1e3, "ms_per_frame_all": [t * 1e3 for t in times],
+            "value": iters * float(n) * n / best / 1e9, "unit": METRIC, "cores": o.num_threads(),
+            "kind": "port", "timing": "host clock around the whole frame (10 fused force+integrate iterations)"}
 
 
 def run_reference_arm(args, dist, emit):
     """--impl reference: the CPU port on all host threads, rank 0 only."""
     if dist.rank != 0:
         return
-    n = args.bodies or (1048576 if args.gpus == 1 else 4194304)
+    n = workload_size(args)
     import oracle_lib
     if not os.path.exists(oracle_lib.ORACLE_LIB):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
@@ -218,16 +260,58 @@ def run_reference_arm(args, dist, emit):
         o.time_accel(st[0], st[1], st[2], 1.0e-7, 0, i_sample, 1)
     dt = time.perf_counter() - t0
     g = args.steps * i_sample * n / dt / 1e9
-    sample = (f"each step = forces of {i_sample} of the {n} bodies against all {n} "
-              f"(C/OpenMP restatement of the reference's SYCL/OpenCL-CPU kernel; nbody_dpcpp itself cannot be built here)")
+    sample = (f"each step = forces of {i_sample} of the {n} bodies against all {n}, i.e. {i_sample / n:.4f} of a full step, "
+              f"rate-normalised to the same metric (a full CPU step of this N would take {n / i_sample * dt / args.steps:.0f} s); "
+              f"C/OpenMP restatement of the reference's SYCL/OpenCL-CPU kernel; nbody_dpcpp itself cannot be built here")
     line = {"impl": "reference", "metric": METRIC, "value": g, "unit": "G inter/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": f"disk galaxy N={n}, SimParam defaults, bounded i-sample", "n_bodies": n},
-            "cpu_baseline": {"value": g, "unit": "G inter/s", "cores": o.num_threads(), "kind": "port", "sample": sample},
+            "data": "synthetic", "config": {"workload": f"disk galaxy N={n}, SimParam defaults, bounded i-sample", "n_bodies": n,
+                                            "sample_fraction_of_a_step": i_sample / n, "same_config_as_gpu_arm": False},
+            "cpu_baseline": {"value": g, "unit": "G inter/s", "cores": o.num_threads(), "kind": "port", "sample": sample,
+                             "cpu_model": cpu_model(), "config0": cpu_config0(o)},
             "e2e": {"value": g, "unit": "G inter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def workload_size(args) -> int:
+    if args.weak_base:
+        return max(256, int(round(args.weak_base * math.sqrt(args.gpus) / 256.0)) * 256)
+    return args.bodies or (1048576 if args.gpus == 1 else 4194304)
+
+
+def golden_force_hash(n: int):
+    try:
+        meta = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_meta.json")))
+        return meta.get("force_sha256", {}).get(str(n))
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def parity_check(sim, n, np):
+    """One force pass of the (sharded) handle against the reference kernel's committed golden."""
+    a = sim.computeAccel()
+    got = hashlib.sha256(np.stack(a, axis=1).reshape(-1).tobytes()).hexdigest()
+    want = golden_force_hash(n)
+    c64 = [c.astype(np.float64) for c in a]
+    third_law = max(abs(c.sum()) / max(np.abs(c).sum(), 1e-300) for c in c64)
+    return {"force_sha256": got, "reference_golden_sha256": want,
+            "matches_reference_golden": (got == want) if want else None,
+            "oracle": "unmodified reference kernel (/root/reference/src/simulator.cu:186-229) on B200, "
+                      "tests/golden/make_golden.py --big-only" if want else "no committed golden for this N",
+            "sum_F_over_sum_absF": third_law}
+
+
+def traffic_for(n_gpus: int, n: int):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture OF THIS CONFIG, else None."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        t = json.load(open(p))
+        e = t.get(f"{n_gpus}x{n}")
+        return (e or {}).get("dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def run_b200_arm(args, dist, emit):
@@ -239,7 +323,7 @@ def run_b200_arm(args, dist, emit):
     nb.load_library()  # raises if the CUDA library is not built -- no fallback
     if nb.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device visible; the product has no CPU path")
-    n = args.bodies or (1048576 if args.gpus == 1 else 4194304)
+    n = workload_size(args)
     params = nb.SimParam(numParticles=n, simIterationsPerFrame=1)
     multi_proc = dist.active
     if multi_proc:
@@ -254,6 +338,12 @@ def run_b200_arm(args, dist, emit):
     def l2_flush():
         flush.zero_()
         torch.cuda.synchronize(dev)
+
+    # ---- parity first: a fast wrong kernel is not measured --------------------------------------
+    parity = parity_check(sim, n, np)  # collective in rank mode
+    if parity["matches_reference_golden"] is False:
+        raise SystemExit(f"bench.py: forces at N={n} on {args.gpus} GPU(s) differ from the reference golden "
+                         f"({parity['force_sha256']} != {parity['reference_golden_sha256']})")
 
     warmup = max(3, args.warmup)
     for _ in range(warmup):
@@ -284,34 +374,64 @@ def run_b200_arm(args, dist, emit):
     value = args.steps * float(n) * n / (dev_ms * 1e-3) / 1e9
 
     # ---- end to end through the C ABI with pinned host buffers -----------------------------------
+    b0, cnt = sim.localRange()
     host = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(6)]
     hv = [t.numpy() for t in host]
-    sim.readInto(*hv)
+    sim.readInto(*hv)  # full state once: every rank uploads all N positions below
+    if multi_proc:
+        loc = [torch.empty(cnt, dtype=torch.float32).pin_memory() for _ in range(6)]
+        lv = [t.numpy() for t in loc]
+
+    def read_back():
+        if multi_proc:
+            sim.readLocalInto(*lv)  # this rank's bodies: positions + velocities
+        else:
+            sim.readInto(*hv)       # D2H: positions + velocities, SoA, as recvFromDevice does
+
     e2e_steps = max(2, min(args.steps, 5))
     sim.setState(*hv)
     sim.stepSim()
-    sim.readInto(*hv)  # warm
+    read_back()  # warm
     dist.barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         sim.setState(*hv)          # H2D: positions (all N) + velocities (owned shard)
         sim.stepSim()              # one iteration
-        sim.readInto(*hv)          # D2H: positions + velocities, SoA, as recvFromDevice does
+        read_back()
     torch.cuda.synchronize(dev)
     dist.barrier()
     e2e_s = dist.max(time.perf_counter() - t0)
     e2e_value = e2e_steps * float(n) * n / e2e_s / 1e9
-    ranks = dist.world if multi_proc else 1
     if multi_proc:
         h2d = sum(12 * n + 12 * nb.plan_shard(n, dist.world, r)[1] for r in range(dist.world))
-        d2h = 24 * n * dist.world
+        d2h = 24 * n  # every body's position + velocity is read back exactly once, by its owner
     else:
         h2d = 12 * n * args.gpus + 12 * n
         d2h = 24 * n
 
     kname = sim.kernelName()
     sim.close()
+
+    # ---- same-N single-GPU point for the scaling curve (rank 0, outside every timed region) ------
+    same_n = None
+    if args.gpus > 1 and dist.rank == 0 and not args.no_same_n and float(n) * n <= 1.8e13:
+        try:
+            one = nb.DiskGalaxySimulator(params, n_gpus=1) if not multi_proc else \
+                nb.DiskGalaxySimulator(params, rank=0, world=1, device=dist.local_rank)
+            one.stepSim()
+            ms = []
+            for _ in range(2):
+                l2_flush()
+                one.stepSim()
+                ms.append(one.getLastStepDeviceTime())
+            one.close()
+            v1 = float(n) * n / (sum(ms) / len(ms) * 1e-3) / 1e9
+            same_n = {"value_same_n_1gpu": v1, "ms_per_step_1gpu": sum(ms) / len(ms), "steps": len(ms),
+                      "efficiency_same_n": value / (args.gpus * v1)}
+        except Exception as e:  # noqa: BLE001
+            same_n = {"error": str(e)}
+    dist.barrier()
     if dist.rank != 0:
         return
 
@@ -324,52 +444,71 @@ def run_b200_arm(args, dist, emit):
     alg_bytes = n * 16 + (n / n_gpus) * 48
     hbm_gbs = alg_bytes / (dev_ms / args.steps * 1e-3) / 1e9
     roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None,
+                "frac": achieved_tf / peak_tf, "traffic": traffic_for(n_gpus, n),
                 "peak_source": f"148 SMs x 128 FP32 lanes x 2 flop x sm_max_mhz of MEASURED_PEAKS.json ({peak_src})",
                 "convention": "20 flop/interaction (north_star); the exact 12-op recipe is FMA-pipe bound at 83.3% of this",
                 "per_gpu": True,
                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": peaks.get("hbm_gbs"), "frac": hbm_gbs / peaks.get("hbm_gbs", 6448.4),
                         "algorithmic_bytes_per_step_per_gpu": alg_bytes},
-                "note": "path is FP32-FMA-pipe bound, neither HBM nor tensor: see DESIGN.md section 5"}
-    # dram traffic of the dominant kernel from the committed ncu capture, if present
-    tr = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tr):
-        try:
-            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
-        except Exception:  # noqa: BLE001
-            pass
+                "note": "path is FP32-FMA-pipe / register-file bound, neither HBM nor tensor: see DESIGN.md section 5; "
+                        "traffic = dram bytes per launch from the ncu capture of THIS config (profiles/r02_traffic.json) or null"}
 
+    if args.weak_base:
+        cfg_name = f"weak scaling in work: N = {args.weak_base}*sqrt(gpus) (BASELINE.json configs[4])"
+    elif n == 1048576 and n_gpus == 1:
+        cfg_name = "BASELINE.json configs[2]"
+    elif n == 4194304:
+        cfg_name = "BASELINE.json configs[3]"
+    elif n == 16777216:
+        cfg_name = "BASELINE.json configs[4] (strong)"
+    elif n == 262144:
+        cfg_name = "BASELINE.json configs[1]"
+    else:
+        cfg_name = "custom size"
     line = {"metric": METRIC, "value": value, "unit": "G inter/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak" if args.weak_base else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"reference disk galaxy (mt19937 seed 5489), N={n}, SimParam defaults, "
                                    f"1 force+integrate iteration per step",
                        "n_bodies": n, "kernel": kname, "sharding": f"i-range x{n_gpus}" if n_gpus > 1 else "none",
                        "process_model": "torchrun, one rank per GPU" if multi_proc else "single process",
                        "l2": "flushed between timed steps (256 MiB memset)",
-                       "baseline_config": "BASELINE.json configs[2]" if n_gpus == 1 else "BASELINE.json configs[3]"},
+                       "baseline_config": cfg_name},
             "pct_fp32_roofline": 100.0 * achieved_tf / peak_tf,
             "roofline": roofline,
+            "parity": parity,
             "e2e": {"value": e2e_value, "unit": "G inter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                    "path": "nbody_set_state(pinned host SoA) + nbody_step + nbody_read_pos/vel(pinned host SoA)"},
+                    "path": "nbody_set_state(pinned host SoA) + nbody_step + " +
+                            ("nbody_read_local(pinned host SoA, the rank's own bodies)" if multi_proc
+                             else "nbody_read_state(pinned host SoA)")},
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
             "ms_per_step_each": per_step}
+    if same_n is not None:
+        line["same_n_scaling"] = same_n
     if n_gpus == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(n)
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"error": str(e)}
-    if n_gpus == 1 and not args.no_ref_kernel:
+    if n_gpus == 1 and not args.no_ref_kernel and float(n) * n <= 2e12:
         try:
             import refsim
             if refsim.available():
                 r = refsim.RefSimulator(n, iters=1)
-                r.time_kernel(64, 1)
-                ms = r.time_kernel(64, 2) / 2
+                per_gw = {}
+                for gw in (64, 128, 256):  # the reference's default (sim_param.cpp:20) and the README's table sizes
+                    r.time_kernel(gw, 1)
+                    per_gw[str(gw)] = r.time_kernel(gw, 3) / 3
                 r.close()
+                gw_best = min(per_gw, key=per_gw.get)
+                ms = per_gw[gw_best]
                 line["reference_cuda_kernel"] = {"value": float(n) * n / ms / 1e6, "unit": "G inter/s", "ms_per_step": ms,
-                                                 "what": "unmodified particle_interaction<BRANCH> (oracle/_ref), gwSize 64, same GPU, same N"}
+                                                 "gw_size_best": int(gw_best), "ms_per_step_by_gw_size": per_gw,
+                                                 "launches_timed_per_gw_size": 3,
+                                                 "what": "unmodified particle_interaction<BRANCH> (oracle/_ref), best of gwSize 64/128/256, "
+                                                         "same GPU, same N, CUDA events, after this arm's timed region",
+                                                 "speedup_of_this_repo": value / (float(n) * n / ms / 1e6)}
         except Exception as e:  # noqa: BLE001
             line["reference_cuda_kernel"] = {"error": str(e)}
     emit(line)
@@ -391,6 +530,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bodies", type=int, default=0)
+    ap.add_argument("--weak-base", type=int, default=0, help="weak scaling in work: N = base*sqrt(gpus)")
+    ap.add_argument("--no-same-n", action="store_true", help="skip the same-N single-GPU point of multi-GPU runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-kernel", action="store_true")
     args = ap.parse_args()

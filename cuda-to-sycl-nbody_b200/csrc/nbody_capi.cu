@@ -6,8 +6,9 @@
 //   pos[2]   full-N float4 (x,y,z,mass) replicas, double buffered like pos_d/pos_next_d
 //   vel      float4 per OWNED body (contiguous i-shard [i_begin, i_begin+i_count))
 //   acc      float4 per owned body: accumulators carried between j-chunk launches
-//   stage[3] N floats each: SoA staging for the reference's ParticleData host layout
-//   compute stream: force+integrate launches; comm stream: NCCL broadcasts of the new shard
+//   stage[3] N floats each (+ vstage[3], owned bodies): SoA staging for the reference's ParticleData host layout
+//   compute stream: force+integrate launches; comm stream: NCCL broadcasts of the new shard;
+//   copy stream: device->host copies of a read-back, overlapped with the velocity de-interleave
 //
 // Multi-GPU iteration (bit-exact w.r.t. one GPU): the j-loop is cut into `world` chunks in
 // ascending rank order = ascending j order; chunk c is launched as soon as the broadcast of
@@ -105,14 +106,16 @@ struct DeviceCtx {
   int rank = 0;  // global rank of this shard
   uint32_t i_begin = 0, i_count = 0;
   int sms = 0;
-  cudaStream_t compute = nullptr, comm = nullptr;
+  cudaStream_t compute = nullptr, comm = nullptr, copy = nullptr;
   float4 *pos[2] = {nullptr, nullptr};
   float4 *vel = nullptr, *acc = nullptr;
   float4 *gather = nullptr;  // lazily allocated full-N scratch (velocity / accel gathers)
   float *stage[3] = {nullptr, nullptr, nullptr};
+  float *vstage[3] = {nullptr, nullptr, nullptr};  // second staging triple (owned bodies): velocity read-back
   float *mass = nullptr;  // optional staging for masses
   ncclComm_t nccl = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_computed = nullptr, ev_comm_done = nullptr;
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};  // staging triple filled (read-back pipeline)
   std::vector<cudaEvent_t> chunk_ready;
   // peer-push exchange: every rank's two position replicas as seen from this device
   // (own pointers, cudaDeviceEnablePeerAccess mappings, or cudaIpcOpenMemHandle mappings)
@@ -120,8 +123,8 @@ struct DeviceCtx {
   std::vector<void *> ipc_opened;
   cudaEvent_t iter_done[2] = {nullptr, nullptr};
   float *barrier_word = nullptr;  // 1 float, NCCL all-reduce used as a device-side barrier (rank mode)
-  unsigned int *progress = nullptr;  // j-segment hand-off words, one per 64 owned bodies
-  unsigned int epoch = 0;            // running segment counter of this device's launches
+  nbody::SegSync sync;               // j-segment hand-off words + ticket counter + error word of this device
+  unsigned int *error_host = nullptr;  // host side of sync.error (mapped pinned memory)
   nbody::KernelConfig cfg{};
   std::string name;
 };
@@ -179,10 +182,17 @@ int alloc_device(nbody_handle *h, DeviceCtx &d) {
   CK(cudaMalloc(&d.pos[1], n * sizeof(float4)));
   CK(cudaMalloc(&d.vel, own * sizeof(float4)));
   CK(cudaMalloc(&d.acc, own * sizeof(float4)));
-  const size_t words = own / 64 + 2;
-  CK(cudaMalloc(&d.progress, words * sizeof(unsigned int)));
-  CK(cudaMemset(d.progress, 0, words * sizeof(unsigned int)));
+  // hand-off state of the j-segmented launches: [0] ticket counter, then one word per 64 owned bodies
+  d.sync.n_groups = (uint32_t)(own / 64 + 2);
+  CK(cudaMalloc(&d.sync.words, ((size_t)d.sync.n_groups + 1) * sizeof(unsigned int)));
+  CK(cudaMemset(d.sync.words, 0, ((size_t)d.sync.n_groups + 1) * sizeof(unsigned int)));
+  CK(cudaHostAlloc(&d.error_host, sizeof(unsigned int), cudaHostAllocMapped));
+  *d.error_host = 0;
+  CK(cudaHostGetDevicePointer(&d.sync.error, d.error_host, 0));
   for (int k = 0; k < 3; k++) CK(cudaMalloc(&d.stage[k], n * sizeof(float)));
+  for (int k = 0; k < 3; k++) CK(cudaMalloc(&d.vstage[k], own * sizeof(float)));
+  CK(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
+  for (auto &e : d.ev_stage) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CK(cudaEventCreate(&d.ev_start));
   CK(cudaEventCreate(&d.ev_stop));
   CK(cudaEventCreateWithFlags(&d.ev_computed, cudaEventDisableTiming));
@@ -197,6 +207,7 @@ int sync_all(nbody_handle *h) {
     CK(cudaSetDevice(d.device));
     CK(cudaStreamSynchronize(d.compute));
     CK(cudaStreamSynchronize(d.comm));
+    if (d.copy) CK(cudaStreamSynchronize(d.copy));
   }
   return 0;
 }
@@ -243,8 +254,7 @@ int enqueue_pass(nbody_handle *h, int src, int flags_last, bool wait_chunks) {
     a.G = h->p.G;
     a.damping = h->p.damping;
     a.n_peers = 0;
-    a.progress = d.progress;
-    a.epoch = &d.epoch;
+    a.sync = &d.sync;
     if (h->world == 1 || h->exchange == 1) {
       // one launch over all j.  Peer push: the epilogue stores the new positions into every
       // other rank's next-position replica as well (not for the accel dump, which moves nothing)
@@ -293,14 +303,22 @@ int upload_soa(nbody_handle *h, DeviceCtx &d, const float *x, const float *y, co
   return 0;
 }
 
+// float4 device array -> three host arrays.  The de-interleave runs on the compute stream into one of
+// the two staging triples (which = 0: N floats each; 1: owned-body count each), the three copies go to
+// the COPY stream behind an event, so the de-interleave of the next array overlaps them.  Asynchronous:
+// the caller ends with sync_all().  With registered / pinned host memory (nbody_host_register) the
+// copies are true DMA transfers; with pageable memory the driver stages them.
 int download_soa(nbody_handle *h, DeviceCtx &d, const float4 *src, uint32_t count, float *x, float *y,
-                 float *z) {
+                 float *z, int which = 0) {
   if (count == 0) return 0;
-  CK(nbody::launch_deinterleave(src, d.stage[0], d.stage[1], d.stage[2], count, d.compute));
+  float *const *st = which ? d.vstage : d.stage;
+  CK(nbody::launch_deinterleave(src, st[0], st[1], st[2], count, d.compute));
   h->launches++;
-  CK(cudaMemcpyAsync(x, d.stage[0], count * sizeof(float), cudaMemcpyDeviceToHost, d.compute));
-  CK(cudaMemcpyAsync(y, d.stage[1], count * sizeof(float), cudaMemcpyDeviceToHost, d.compute));
-  CK(cudaMemcpyAsync(z, d.stage[2], count * sizeof(float), cudaMemcpyDeviceToHost, d.compute));
+  CK(cudaEventRecord(d.ev_stage[which], d.compute));
+  CK(cudaStreamWaitEvent(d.copy, d.ev_stage[which], 0));
+  CK(cudaMemcpyAsync(x, st[0], count * sizeof(float), cudaMemcpyDeviceToHost, d.copy));
+  CK(cudaMemcpyAsync(y, st[1], count * sizeof(float), cudaMemcpyDeviceToHost, d.copy));
+  CK(cudaMemcpyAsync(z, st[2], count * sizeof(float), cudaMemcpyDeviceToHost, d.copy));
   return 0;
 }
 
@@ -338,7 +356,7 @@ int read_sharded(nbody_handle *h, int which /*0 = vel, 1 = acc*/, float *x, floa
       CK(cudaMemcpyAsync(f4 + 4 * (size_t)d.i_begin, src, (size_t)d.i_count * sizeof(float4),
                          cudaMemcpyDeviceToHost, d.compute));
     } else {
-      int rc = download_soa(h, d, src, d.i_count, x + d.i_begin, y + d.i_begin, z + d.i_begin);
+      int rc = download_soa(h, d, src, d.i_count, x + d.i_begin, y + d.i_begin, z + d.i_begin, 1);
       if (rc) return rc;
     }
   }
@@ -456,8 +474,9 @@ int create_common(const nbody_params *p, const std::vector<int> &devices, int fi
   if (p->num_particles == 0 || p->num_particles >= (1ull << 31))
     return fail(NBODY_E_INVALID, "num_particles must be in [1, 2^31)");
   if (p->iters_per_frame < 0) return fail(NBODY_E_INVALID, "iters_per_frame < 0");
-  if (p->calc_method != NBODY_CALC_BRANCH && p->calc_method != NBODY_CALC_PREDICATED)
-    return fail(NBODY_E_INVALID, "calc_method must be BRANCH or PREDICATED");
+  if (p->calc_method != NBODY_CALC_BRANCH && p->calc_method != NBODY_CALC_PREDICATED &&
+      p->calc_method != NBODY_CALC_PREDICATED_FIXED)
+    return fail(NBODY_E_INVALID, "calc_method must be BRANCH, PREDICATED or PREDICATED_FIXED");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -609,7 +628,12 @@ int nbody_destroy(nbody_handle *h) {
     cudaFree(d.gather);
     cudaFree(d.mass);
     cudaFree(d.barrier_word);
-    cudaFree(d.progress);
+    cudaFree(d.sync.words);
+    if (d.error_host) cudaFreeHost(d.error_host);
+    for (int k = 0; k < 3; k++) cudaFree(d.vstage[k]);
+    for (cudaEvent_t e : d.ev_stage)
+      if (e) cudaEventDestroy(e);
+    if (d.copy) cudaStreamDestroy(d.copy);
     for (void *p : d.ipc_opened) cudaIpcCloseMemHandle(p);
     for (cudaEvent_t e : d.iter_done)
       if (e) cudaEventDestroy(e);
@@ -635,6 +659,8 @@ int nbody_set_kernel(nbody_handle *h, int kernel) {
                 "unpredicated kernels are not bit-exact for this distEps / calcMethod; use AUTO or GENERIC");
   if ((kernel == NBODY_KERNEL_PACKED || kernel == NBODY_KERNEL_SCALAR) && h->has_mass)
     return fail(NBODY_E_STATE, "per-body masses need the AUTO or GENERIC kernel");
+  if ((kernel == NBODY_KERNEL_PACKED || kernel == NBODY_KERNEL_SCALAR) && !nbody::variants_built())
+    return fail(NBODY_E_INVALID, "the CTA-tiled comparison kernels are only in libnbody_b200_variants.so (make VARIANTS=1)");
   h->kernel = kernel;
   refresh_configs(h);
   return 0;
@@ -701,6 +727,15 @@ int nbody_step(nbody_handle *h) {
     CK(cudaSetDevice(d.device));
     CK(cudaEventRecord(d.ev_start, d.compute));
   }
+  if (iters > 0 && h->world > 1 && h->exchange == 1 && (int)h->devs.size() < h->world) {
+    // one process per GPU, peer push: this rank's first kernel stores into every OTHER rank's
+    // next-position replica.  Those ranks may still be reading that buffer (a read-back or state
+    // dump of the previous frame, or nbody_set_state), so every rank joins a device-side barrier
+    // before the frame's first launch -- nbody_step is collective over the ranks.
+    DeviceCtx &d = h->devs[0];
+    CK(cudaSetDevice(d.device));
+    NK(g_nccl.AllReduce(d.barrier_word, d.barrier_word, 1, ncclFloat, ncclMin, d.nccl, d.compute));
+  }
   for (int it = 0; it < iters; it++) {
     int rc = enqueue_pass(h, h->cur, nbody::kLastChunk, !h->replicas_fresh);
     if (rc) return rc;
@@ -762,6 +797,13 @@ int nbody_step(nbody_handle *h) {
     }
   }
   h->last_dev_ms = mx;
+  for (auto &d : h->devs)
+    if (d.error_host && *(volatile unsigned int *)d.error_host) {
+      *d.error_host = 0;
+      return fail(NBODY_E_STATE, "device %d: a j-segment hand-off wait exceeded 20 s (GPU time-sliced or halted by a "
+                                 "debugger?); the state of this handle is no longer valid -- reload it with nbody_set_state",
+                  d.device);
+    }
   return 0;
 }
 
@@ -794,6 +836,55 @@ int nbody_read_vel(nbody_handle *h, float *vx, float *vy, float *vz) {
 int nbody_read_vel_f4(nbody_handle *h, float *xyzw) {
   if (!h || !xyzw) return fail(NBODY_E_INVALID, "null argument");
   return read_sharded(h, 0, nullptr, nullptr, nullptr, xyzw);
+}
+
+int nbody_read_state(nbody_handle *h, float *x, float *y, float *z, float *vx, float *vy, float *vz) {
+  if (!h || !x || !y || !z || !vx || !vy || !vz) return fail(NBODY_E_INVALID, "null argument");
+  if (h->world > (int)h->devs.size()) {  // other processes own some shards: gather the velocities first
+    int rc = nbody_read_pos(h, x, y, z);
+    return rc ? rc : nbody_read_vel(h, vx, vy, vz);
+  }
+  DeviceCtx &d0 = h->devs[0];
+  CK(cudaSetDevice(d0.device));
+  int rc = download_soa(h, d0, d0.pos[h->cur], h->n, x, y, z, 0);
+  if (rc) return rc;
+  for (auto &d : h->devs) {  // velocity de-interleave overlaps the position copies
+    CK(cudaSetDevice(d.device));
+    if ((rc = download_soa(h, d, d.vel, d.i_count, vx + d.i_begin, vy + d.i_begin, vz + d.i_begin, 1))) return rc;
+  }
+  return sync_all(h);
+}
+
+int nbody_local_range(nbody_handle *h, uint64_t *begin, uint64_t *count) {
+  if (!h || !begin || !count || h->devs.empty()) return fail(NBODY_E_INVALID, "null argument");
+  *begin = h->devs.front().i_begin;
+  *count = (uint64_t)h->devs.back().i_begin + h->devs.back().i_count - *begin;
+  return 0;
+}
+
+int nbody_read_local(nbody_handle *h, float *x, float *y, float *z, float *vx, float *vy, float *vz) {
+  if (!h || !x || !y || !z || !vx || !vy || !vz) return fail(NBODY_E_INVALID, "null argument");
+  const size_t b0 = h->devs.front().i_begin;
+  for (auto &d : h->devs) {  // every device serves its own shard from its own replica: parallel PCIe links
+    CK(cudaSetDevice(d.device));
+    const size_t o = d.i_begin - b0;
+    int rc = download_soa(h, d, d.pos[h->cur] + d.i_begin, d.i_count, x + o, y + o, z + o, 0);
+    if (!rc) rc = download_soa(h, d, d.vel, d.i_count, vx + o, vy + o, vz + o, 1);
+    if (rc) return rc;
+  }
+  return sync_all(h);
+}
+
+int nbody_host_register(void *ptr, size_t bytes) {
+  if (!ptr || !bytes) return fail(NBODY_E_INVALID, "null argument");
+  CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+
+int nbody_host_unregister(void *ptr) {
+  if (!ptr) return fail(NBODY_E_INVALID, "null argument");
+  CK(cudaHostUnregister(ptr));
+  return 0;
 }
 
 int nbody_compute_accel(nbody_handle *h, float *ax, float *ay, float *az) {
@@ -875,7 +966,7 @@ int nbody_num_gpus(nbody_handle *h) { return h ? (int)h->devs.size() : 0; }
 int nbody_world_size(nbody_handle *h) { return h ? h->world : 0; }
 
 int nbody_launch_step_device(const nbody_params *p, const void *pos4, void *vel4, void *pos4_next,
-                             uint64_t i_begin, uint64_t i_count, int kernel, void *cuda_stream) {
+                             uint64_t i_begin, uint64_t i_count, int kernel, int flags, void *cuda_stream) {
   if (!p || !pos4 || !vel4 || !pos4_next) return fail(NBODY_E_INVALID, "null argument");
   if (p->num_particles == 0 || p->num_particles >= (1ull << 31) || i_begin + i_count > p->num_particles)
     return fail(NBODY_E_INVALID, "bad body range");
@@ -885,7 +976,13 @@ int nbody_launch_step_device(const nbody_params *p, const void *pos4, void *vel4
   if ((kernel == NBODY_KERNEL_PACKED || kernel == NBODY_KERNEL_SCALAR) &&
       (p->calc_method != NBODY_CALC_BRANCH || !nbody::eps_allows_unpredicated(p->dist_eps)))
     return fail(NBODY_E_INVALID, "unpredicated kernels are not bit-exact for this distEps / calcMethod");
-  nbody::KernelConfig cfg = nbody::choose_config(kernel, p->calc_method, p->dist_eps, (uint32_t)i_count, sms, false);
+  if ((kernel == NBODY_KERNEL_PACKED || kernel == NBODY_KERNEL_SCALAR) && !nbody::variants_built())
+    return fail(NBODY_E_INVALID, "the CTA-tiled comparison kernels are only in libnbody_b200_variants.so (make VARIANTS=1)");
+  if (flags & ~NBODY_DEVSTEP_MASS) return fail(NBODY_E_INVALID, "unknown flags");
+  const bool has_mass = (flags & NBODY_DEVSTEP_MASS) != 0;
+  if (has_mass && (kernel == NBODY_KERNEL_PACKED || kernel == NBODY_KERNEL_SCALAR))
+    return fail(NBODY_E_INVALID, "per-body masses need the AUTO or GENERIC kernel");
+  nbody::KernelConfig cfg = nbody::choose_config(kernel, p->calc_method, p->dist_eps, (uint32_t)i_count, sms, has_mass);
   nbody::StepArgs a;
   a.pos = (const float4 *)pos4;
   a.pos_next = (float4 *)pos4_next;
@@ -902,8 +999,7 @@ int nbody_launch_step_device(const nbody_params *p, const void *pos4, void *vel4
   a.damping = p->damping;
   a.flags = nbody::kFirstChunk | nbody::kLastChunk;
   a.n_peers = 0;
-  a.progress = nullptr;
-  a.epoch = nullptr;
+  a.sync = nullptr;  // no hand-off buffers with caller-owned memory: one j-segment per body group
   CK(nbody::launch_step(cfg, a, (cudaStream_t)cuda_stream));
   return 0;
 }

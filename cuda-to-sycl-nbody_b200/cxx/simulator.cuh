@@ -52,7 +52,9 @@ class Simulator {
 // stepSim().  The read-back is lazy: the device->host copy happens on the first getter call
 // after a step (the headless main loop never asks, src/nbody.cpp:95-123).
 // Extra knobs come from the environment so that the constructor signature stays the
-// reference's: NBODY_GPUS=<n> shards the bodies over n GPUs of this process.
+// reference's: NBODY_GPUS=<n> shards the bodies over n GPUs of this process; NBODY_PREDICATED_FIXED=1
+// gives calcMethod PREDICATED the README's (i != id) meaning; NBODY_DUMP_HASH=1 prints the FNV-1a-64
+// hash of the final host state on stderr when the simulator is destroyed.
 class DiskGalaxySimulator : public Simulator {
  public:
   explicit DiskGalaxySimulator(SimParam params_);
@@ -85,6 +87,7 @@ class DiskGalaxySimulator : public Simulator {
   ParticleData vel;
   bool hostFresh{false};
   nbody_handle *impl{nullptr};
+  std::vector<void *> registered;  // host vectors page-locked through nbody_host_register
 };
 
 }  // namespace simulation

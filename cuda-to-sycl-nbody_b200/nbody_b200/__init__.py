@@ -20,8 +20,12 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libnbody_b200.so"))
+# the same library plus the comparison kernels (make VARIANTS=1); tests of those kernels load it explicitly
+VARIANTS_LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libnbody_b200_variants.so"))
 
-CALC_BRANCH, CALC_PREDICATED = 0, 1
+CALC_BRANCH, CALC_PREDICATED, CALC_PREDICATED_FIXED = 0, 1, 2
+DEVSTEP_MASS = 1
+ABI_VERSION = 2
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_PACKED, KERNEL_SCALAR = 0, 1, 2, 3
 
 # every symbol include/nbody_b200.h declares (checked by tests/test_capi_cpu.py)
@@ -31,6 +35,7 @@ ABI_SYMBOLS = [
     "nbody_destroy", "nbody_set_kernel", "nbody_kernel_name", "nbody_set_state", "nbody_set_mass",
     "nbody_step", "nbody_last_step_ms", "nbody_last_step_device_ms", "nbody_launch_count",
     "nbody_read_pos", "nbody_read_vel", "nbody_read_pos_f4", "nbody_read_vel_f4",
+    "nbody_read_state", "nbody_local_range", "nbody_read_local", "nbody_host_register", "nbody_host_unregister",
     "nbody_save_state", "nbody_load_state",
     "nbody_device_name", "nbody_num_particles", "nbody_num_gpus", "nbody_world_size",
     "nbody_compute_accel", "nbody_launch_step_device",
@@ -117,6 +122,11 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.nbody_read_vel.argtypes = [H] + [_fp] * 3
     lib.nbody_read_pos_f4.argtypes = [H, _fp]
     lib.nbody_read_vel_f4.argtypes = [H, _fp]
+    lib.nbody_read_state.argtypes = [H] + [_fp] * 6
+    lib.nbody_local_range.argtypes = [H, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    lib.nbody_read_local.argtypes = [H] + [_fp] * 6
+    lib.nbody_host_register.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    lib.nbody_host_unregister.argtypes = [ctypes.c_void_p]
     lib.nbody_save_state.argtypes = [H, ctypes.c_char_p]
     lib.nbody_load_state.argtypes = [H, ctypes.c_char_p]
     lib.nbody_device_name.argtypes = [H]
@@ -128,7 +138,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.nbody_compute_accel.argtypes = [H] + [_fp] * 3
     lib.nbody_launch_step_device.argtypes = [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64,
-                                             ctypes.c_int, ctypes.c_void_p]
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     if path is None:
         _lib = lib
     return lib
@@ -183,8 +193,8 @@ class DiskGalaxySimulator:
     """Mirror of simulation::DiskGalaxySimulator (reference src/simulator.cuh:129-160)."""
 
     def __init__(self, params: SimParam, n_gpus: int = 1, *, rank: int | None = None,
-                 world: int | None = None, device: int = 0, unique_id: bytes | None = None):
-        self._lib = load_library()
+                 world: int | None = None, device: int = 0, unique_id: bytes | None = None, lib=None):
+        self._lib = lib if lib is not None else load_library()
         self.params = params
         self._h = ctypes.c_void_p()
         cp = params.to_c()
@@ -283,8 +293,18 @@ class DiskGalaxySimulator:
 
     def readInto(self, x, y, z, vx, vy, vz):
         """Read-back into caller buffers (e.g. pinned memory) -- recvFromDevice, src/simulator.cu:106-129."""
-        _check(self._lib, self._lib.nbody_read_pos(self._h, _ptr(x), _ptr(y), _ptr(z)), "nbody_read_pos")
-        _check(self._lib, self._lib.nbody_read_vel(self._h, _ptr(vx), _ptr(vy), _ptr(vz)), "nbody_read_vel")
+        _check(self._lib, self._lib.nbody_read_state(self._h, *[_ptr(a) for a in (x, y, z, vx, vy, vz)]),
+               "nbody_read_state")
+
+    def localRange(self) -> tuple[int, int]:
+        b, c = ctypes.c_uint64(), ctypes.c_uint64()
+        _check(self._lib, self._lib.nbody_local_range(self._h, ctypes.byref(b), ctypes.byref(c)), "nbody_local_range")
+        return int(b.value), int(c.value)
+
+    def readLocalInto(self, x, y, z, vx, vy, vz):
+        """positions + velocities of the bodies this handle's devices own (count floats per array)"""
+        _check(self._lib, self._lib.nbody_read_local(self._h, *[_ptr(a) for a in (x, y, z, vx, vy, vz)]),
+               "nbody_read_local")
 
     def close(self):
         if self._h:

@@ -14,7 +14,11 @@
  *     NBODY_E_*); nbody_last_error() returns a static description of the last failure of
  *     the calling thread;
  *   - a handle is NOT re-entrant: one host thread at a time (the reference is single
- *     threaded, src/nbody.cpp:31-141);
+ *     threaded, src/nbody.cpp:31-141); different handles may be driven from different threads;
+ *   - handles made by nbody_create_rank (one process per GPU) have COLLECTIVE calls, which every
+ *     rank must make in the same order: nbody_create_rank, nbody_step, nbody_read_vel[_f4],
+ *     nbody_read_state, nbody_compute_accel, nbody_save_state, nbody_destroy.  nbody_set_state,
+ *     nbody_set_mass, nbody_read_pos[_f4] and nbody_read_local are local to the calling rank;
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
  */
 #ifndef NBODY_B200_H_
@@ -27,7 +31,7 @@
 extern "C" {
 #endif
 
-#define NBODY_B200_ABI_VERSION 1
+#define NBODY_B200_ABI_VERSION 2
 
 /* error codes beyond CUDA's (which are passed through unchanged, all < 10000) */
 #define NBODY_E_INVALID 10001 /* bad argument                                  */
@@ -38,12 +42,19 @@ extern "C" {
 /* calculation method: reference enum CalculationMethod, src/sim_param.hpp:8-11 */
 #define NBODY_CALC_BRANCH     0
 #define NBODY_CALC_PREDICATED 1 /* reproduces the shipped (i == id) behaviour, src/simulator.cu:208-209 */
+/* opt-in extension: PREDICATED as the README describes it, force += r * inv * (i != id)
+ * (README.md:229-231,247-250); bit-exact against the reference built with that one character changed
+ * (oracle/Makefile: ref_fixed).  The C++ class selects it for calcMethod == PREDICATED when the
+ * environment has NBODY_PREDICATED_FIXED=1. */
+#define NBODY_CALC_PREDICATED_FIXED 2
 
 /* kernel selection (new knob; the reference has one kernel) */
 #define NBODY_KERNEL_AUTO    0 /* packed f32x2 kernel when bit-exactness allows, else generic */
 #define NBODY_KERNEL_GENERIC 1 /* scalar, predicated self-term; always valid                  */
-#define NBODY_KERNEL_PACKED  2 /* force the packed kernel (fails if eps makes it inexact)     */
-#define NBODY_KERNEL_SCALAR  3 /* register-blocked scalar FFMA kernel (comparison variant)    */
+/* comparison variants, present only in lib/libnbody_b200_variants.so (make VARIANTS=1); the product
+ * library rejects them with NBODY_E_INVALID */
+#define NBODY_KERNEL_PACKED  2 /* CTA-tiled packed kernel (fails if eps makes it inexact)     */
+#define NBODY_KERNEL_SCALAR  3 /* CTA-tiled register-blocked scalar FFMA kernel               */
 
 /*
  * Mirror of the fields of the reference's SimParam that the hot path reads
@@ -111,7 +122,7 @@ int nbody_nccl_unique_id(void *out128);
 /* frees device, pinned and NCCL resources (the reference never frees: no dtor) */
 int nbody_destroy(nbody_handle *h);
 
-/* kernel variant selection; must be called before the next nbody_step */
+/* kernel selection; must be called before the next nbody_step */
 int nbody_set_kernel(nbody_handle *h, int kernel);
 /* human-readable description of the kernel configuration the next step will use */
 const char *nbody_kernel_name(nbody_handle *h);
@@ -154,6 +165,21 @@ int nbody_read_vel(nbody_handle *h, float *vx, float *vy, float *vz);
 int nbody_read_pos_f4(nbody_handle *h, float *xyzw);
 int nbody_read_vel_f4(nbody_handle *h, float *xyzw);
 
+/* positions and velocities in one call (one de-interleave pass per array, the device->host copies on
+ * a copy stream overlapping the next de-interleave): what stepSim() hands to the host every frame,
+ * src/simulator.cu:74 */
+int nbody_read_state(nbody_handle *h, float *x, float *y, float *z, float *vx, float *vy, float *vz);
+/* the bodies [begin, begin + count) owned by the devices of this handle (all of them for nbody_create;
+ * one rank's shard for nbody_create_rank) and their positions + velocities, count floats per array:
+ * the read-back a rank needs when every process keeps only its own bodies.  Not collective. */
+int nbody_local_range(nbody_handle *h, uint64_t *begin, uint64_t *count);
+int nbody_read_local(nbody_handle *h, float *x, float *y, float *z, float *vx, float *vy, float *vz);
+/* page-lock caller memory (cudaHostRegister) so nbody_set_state / nbody_read_* move it by DMA instead
+ * of through the driver's pageable staging; the C++ class registers its ParticleData vectors once
+ * (they never reallocate, src/simulator.cuh:75-84).  Unregister before freeing the memory. */
+int nbody_host_register(void *ptr, size_t bytes);
+int nbody_host_unregister(void *ptr);
+
 /*
  * Checkpoint / resume (the reference has none).  Little-endian binary file:
  *   char magic[8] = "NBB200\0\1"; uint64 n; float G, dt, damping, dist_eps; int32 iters_per_frame,
@@ -186,11 +212,13 @@ int nbody_compute_accel(nbody_handle *h, float *ax, float *ay, float *az);
  *   vel4      : float4 velocity of bodies [i_begin, i_begin+i_count), indexed from 0
  *   pos4_next : n_bodies float4, entries [i_begin, i_begin+i_count) are written
  * Bodies j in [0, n_bodies) are accumulated in ascending order with one FP32 accumulator per
- * component, exactly as src/simulator.cu:196-211 does.
+ * component, exactly as src/simulator.cu:196-211 does.  flags: 0, or NBODY_DEVSTEP_MASS when pos4[].w
+ * holds per-body masses that are not all 1 (without it w is ignored: the reference is unit-mass).
  */
+#define NBODY_DEVSTEP_MASS 1
 int nbody_launch_step_device(const nbody_params *p, const void *pos4, void *vel4,
                              void *pos4_next, uint64_t i_begin, uint64_t i_count,
-                             int kernel, void *cuda_stream);
+                             int kernel, int flags, void *cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ def test_header_symbols_all_exported(nb):
     for s in declared:
         assert hasattr(lib, s), f"{s} declared in include/nbody_b200.h but not exported"
     assert sorted(nb.ABI_SYMBOLS) == declared, "python binding list out of sync with the header"
-    assert lib.nbody_abi_version() == 1
+    assert lib.nbody_abi_version() == nb.ABI_VERSION == 2
 
 
 def test_library_has_sm100a_code_only(nb):

@@ -11,6 +11,7 @@ difference is 0 ulp; both the contract tolerance and bit equality are asserted.
 """
 from __future__ import annotations
 
+import hashlib
 import json
 import os
 
@@ -25,8 +26,24 @@ ACCEL_TOL = 1e-5   # north_star: per-body single-step accelerations, relative
 POS_TOL = 1e-4     # north_star: positions after 10 steps, relative
 
 
-def _mk(nb, n, **kw):
-    return nb.DiskGalaxySimulator(nb.SimParam(numParticles=n, **kw))
+def _mk(nb, n, lib=None, **kw):
+    return nb.DiskGalaxySimulator(nb.SimParam(numParticles=n, **kw), lib=lib)
+
+
+def sha256_f32(arrays) -> str:
+    """SHA-256 of the float32 byte stream interleaved per body (tests/golden/make_golden.py)."""
+    inter = np.stack([np.ascontiguousarray(a, np.float32) for a in arrays], axis=1).reshape(-1)
+    return hashlib.sha256(inter.tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def vlib(nb):
+    """libnbody_b200_variants.so: the product library plus the comparison kernels (make VARIANTS=1)."""
+    import subprocess
+    if not os.path.exists(nb.VARIANTS_LIB_PATH):
+        subprocess.run(["make", "-C", os.path.dirname(os.path.dirname(nb.VARIANTS_LIB_PATH)), "variants"],
+                       check=True, capture_output=True)
+    return nb.load_library(nb.VARIANTS_LIB_PATH)
 
 
 def _state(sim):
@@ -63,10 +80,11 @@ def test_generator_matches_reference_ctor(nb, ref, n):
 
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("n", [25600, 262144])
-def test_single_step_accelerations_vs_reference(nb, ref, n, kernel):
-    """BASELINE config 2: 262144 bodies, single-step force accuracy vs the reference kernel."""
+def test_single_step_accelerations_vs_reference(nb, vlib, ref, n, kernel):
+    """BASELINE config 2: 262144 bodies, single-step force accuracy vs the reference kernel.
+    "packed" / "scalar" are the CTA-tiled comparison kernels of the VARIANTS library."""
     fx, fy, fz, _ = ref.reference_forces(n)
-    sim = _mk(nb, n)
+    sim = _mk(nb, n, lib=vlib if kernel in ("packed", "scalar") else None)
     sim.setKernel(_kernel_id(nb, kernel))
     a = sim.computeAccel()
     sim.close()
@@ -136,7 +154,7 @@ def test_zero_softening_uses_predicated_self_term(nb, ref):
     r.close()
     sim = _mk(nb, n, simIterationsPerFrame=2, distEps=0.0)
     assert "generic" in sim.kernelName()
-    with pytest.raises(nb.NBodyError):
+    with pytest.raises(nb.NBodyError, match="bit-exact"):
         sim.setKernel(nb.KERNEL_PACKED)
     sim.stepSim()
     got = _state(sim)
@@ -176,10 +194,10 @@ def test_coincident_bodies_and_large_coordinates(nb, ref):
 # ---------------------------------------------------------------------------------------------
 # (2) committed golden fixtures (made by tests/golden/make_golden.py from the reference on a B200)
 # ---------------------------------------------------------------------------------------------
-def test_golden_forces_n2048(nb, golden_dir):
+def test_golden_forces_n2048(nb, vlib, golden_dir):
     g = np.load(os.path.join(golden_dir, "force_n2048.npz"))
     for kernel in KERNELS:
-        sim = _mk(nb, 2048)
+        sim = _mk(nb, 2048, lib=vlib if kernel in ("packed", "scalar") else None)
         sim.setKernel(_kernel_id(nb, kernel))
         _assert_bits(sim.computeAccel(), [g["fx"], g["fy"], g["fz"]], f"golden forces {kernel}")
         sim.close()
@@ -206,6 +224,47 @@ def test_golden_predicated_n1024(nb, golden_dir):
     sim = _mk(nb, 1024, simIterationsPerFrame=1, calcMethod=nb.CALC_PREDICATED)
     sim.stepSim()
     _assert_bits(_state(sim), [g[k] for k in ("x", "y", "z", "vx", "vy", "vz")], "golden predicated")
+    sim.close()
+
+
+def test_golden_predicated_fixed(nb, golden_dir):
+    """README-intended PREDICATED, force += r*inv*(i != id) (README.md:229-231): fixtures from the
+    reference built with src/simulator.cu:209 patched to (i != id) (oracle/Makefile: ref_fixed)."""
+    g = np.load(os.path.join(golden_dir, "predicated_fixed_n1024.npz"))
+    sim = _mk(nb, 1024, simIterationsPerFrame=1, calcMethod=nb.CALC_PREDICATED_FIXED)
+    assert "predicated_fixed" in sim.kernelName()
+    sim.stepSim()
+    _assert_bits(_state(sim), [g[k] for k in ("x", "y", "z", "vx", "vy", "vz")], "golden predicated (fixed)")
+    sim.close()
+    g = np.load(os.path.join(golden_dir, "force_fixed_n2048.npz"))
+    sim = _mk(nb, 2048, calcMethod=nb.CALC_PREDICATED_FIXED)
+    _assert_bits(sim.computeAccel(), [g["fx"], g["fy"], g["fz"]], "golden forces, predicated (fixed)")
+    sim.close()
+    meta = json.load(open(os.path.join(golden_dir, "golden_meta.json")))
+    for n in (25600, 262144):
+        sim = _mk(nb, n, calcMethod=nb.CALC_PREDICATED_FIXED)
+        assert sha256_f32(sim.computeAccel()) == meta["force_fixed_sha256"][str(n)], n
+        sim.close()
+
+
+@pytest.mark.parametrize("n", [25600, 4097])
+def test_predicated_fixed_vs_live_patched_reference(nb, ref, n):
+    """the same against the patched reference running on this GPU (forces and one default step);
+    for the default eps it must also equal BRANCH bit-for-bit only where r*inv*1 + a == fma(r, inv, a)
+    -- it does not in general (FMUL then FFMA rounds twice), which is why it has its own oracle"""
+    if not ref.available("fixed"):
+        pytest.skip("oracle/_ref/libnbody_ref_fixed.so not built")
+    fx, fy, fz, _ = ref.reference_forces(n, calc=1, lib="fixed")
+    sim = _mk(nb, n, calcMethod=nb.CALC_PREDICATED_FIXED)
+    _assert_bits(sim.computeAccel(), [fx, fy, fz], f"forces N={n} predicated-fixed")
+    sim.close()
+    r = ref.RefSimulator(n, iters=3, calc=1, lib="fixed")
+    r.step()
+    want = r.state()
+    r.close()
+    sim = _mk(nb, n, simIterationsPerFrame=3, calcMethod=nb.CALC_PREDICATED_FIXED)
+    sim.stepSim()
+    _assert_bits(_state(sim), want, f"3 steps N={n} predicated-fixed")
     sim.close()
 
 
@@ -255,22 +314,45 @@ def test_cuda_vs_fp64_truth_no_worse_than_contract(nb, oracle):
 # ---------------------------------------------------------------------------------------------
 # full-size properties (BASELINE configs 2/3: N = 1,048,576)
 # ---------------------------------------------------------------------------------------------
-def test_full_size_independent_kernels_agree_and_forces_cancel(nb):
-    """At N=1M the reference kernel itself takes ~0.9 s/step, the CPU oracle hours.  Size-
-    independent checks: two independently written kernels (packed f32x2 vs predicated scalar)
-    agree bit-for-bit on every body, and Newton's third law holds: sum_i F_i ~ 0 relative to
-    sum_i |F_i| (pairwise terms are antisymmetric up to rounding)."""
+def test_full_size_forces_and_step_vs_reference_golden(nb, golden_dir):
+    """BASELINE configs[2], N = 1,048,576: the production kernel (R = 6, j-segmented) against what
+    the UNMODIFIED reference kernel produced for the same galaxy on a B200 -- SHA-256 of all 3M force
+    components and of the full state after one default step (tests/golden/make_golden.py --big-only).
+    Plus Newton's third law as a size-independent sanity property."""
+    meta = json.load(open(os.path.join(golden_dir, "golden_meta.json")))
     n = 1048576
-    sim = _mk(nb, n)
-    sim.setKernel(nb.KERNEL_PACKED)
+    sim = _mk(nb, n, simIterationsPerFrame=1)
+    assert "wseg_f32x2_r6" in sim.kernelName()
     a = sim.computeAccel()
-    sim.setKernel(nb.KERNEL_GENERIC)
-    b = sim.computeAccel()
-    sim.close()
-    _assert_bits(a, b, "packed vs generic at 1M")
+    assert sha256_f32(a) == meta["force_sha256"][str(n)]
     for c in a:
         c64 = c.astype(np.float64)
         assert abs(c64.sum()) <= 1e-3 * np.abs(c64).sum()
+    sim.stepSim()
+    assert sha256_f32(_state(sim)) == meta["step1_sha256"][str(n)]
+    sim.close()
+
+
+@pytest.mark.parametrize("n", [262144, 400003])
+def test_mid_size_forces_vs_reference_golden(nb, golden_dir, n):
+    """configs[1] (262144, R = 4 kernel) and a ragged size just above the R = 6 switch point"""
+    meta = json.load(open(os.path.join(golden_dir, "golden_meta.json")))
+    sim = _mk(nb, n, simIterationsPerFrame=1)
+    assert sha256_f32(sim.computeAccel()) == meta["force_sha256"][str(n)]
+    if str(n) in meta["step1_sha256"]:
+        sim.stepSim()
+        assert sha256_f32(_state(sim)) == meta["step1_sha256"][str(n)]
+    sim.close()
+
+
+def test_generic_kernel_agrees_at_full_size(nb, golden_dir):
+    """the independently written predicated scalar kernel against the same 1M golden"""
+    meta = json.load(open(os.path.join(golden_dir, "golden_meta.json")))
+    n = 1048576
+    sim = _mk(nb, n)
+    sim.setKernel(nb.KERNEL_GENERIC)
+    assert sha256_f32(sim.computeAccel()) == meta["force_sha256"][str(n)]
+    sim.close()
 
 
 def test_device_pointer_entry_matches_handle_path(nb):
@@ -292,7 +374,7 @@ def test_device_pointer_entry_matches_handle_path(nb):
     lib = nb.load_library()
     stream = torch.cuda.current_stream().cuda_stream
     rc = lib.nbody_launch_step_device(ctypes.byref(p), pos4.data_ptr(), vel4.data_ptr(), nxt.data_ptr(),
-                                      0, n, nb.KERNEL_AUTO, stream)
+                                      0, n, nb.KERNEL_AUTO, 0, stream)
     assert rc == 0, lib.nbody_last_error()
     torch.cuda.synchronize()
     got_p, got_v = nxt.cpu().numpy(), vel4.cpu().numpy()
@@ -345,6 +427,26 @@ def test_cxx_dropin_binaries(nb):
         assert [int(line.match(l).group(1)) for l in rows] == [3, 4, 5, 6], rows
         ran += 1
     assert ran >= 1, "no drop-in binary built"
+    # the STATE behind those lines: NBODY_DUMP_HASH=1 makes the C++ class print the FNV-1a-64 of its host
+    # vectors when it is destroyed; it must equal the reference simulator's after the same frames
+    # (covers cxx/simulator.cpp: constructor upload, lazy refreshHost, registered host vectors)
+    import oracle_lib
+    import refsim
+    if refsim.available():
+        r = refsim.RefSimulator(8 * 256, G=2.0, dt=0.001, iters=3, damping=0.999, eps=1.0e-3, gw=128)
+        for _ in range(6):
+            r.step()
+        want = oracle_lib.Oracle().fnv1a64(r.state())
+        r.close()
+        for exe in ("nbody_b200", "nbody_refmain"):
+            path = os.path.join(root, "cuda-to-sycl-nbody_b200", "bin", exe)
+            if not os.path.exists(path):
+                continue
+            env = dict(os.environ, NBODY_DUMP_HASH="1")
+            out = subprocess.run([path, "8", "3", "0.999", "0.001", "1.0e-3", "2.0", "6", "128", "BRANCH"],
+                                 capture_output=True, text=True, timeout=120, env=env)
+            m = re.search(r"final state fnv1a64 ([0-9a-f]{16})", out.stderr)
+            assert m and m.group(1) == want, (exe, out.stderr, want)
     bad = subprocess.run([os.path.join(root, "cuda-to-sycl-nbody_b200", "bin", "nbody_b200"), "8", "1", "1", "1", "1",
                           "1", "1", "64", "NOPE"], capture_output=True, text=True)
     assert bad.returncode != 0  # std::invalid_argument, as the reference (src/sim_param.cpp:36)
@@ -463,16 +565,66 @@ def test_bad_gpu_count_is_rejected(nb):
         nb.DiskGalaxySimulator(nb.SimParam(numParticles=1024), n_gpus=nb.device_count() + 1)
 
 
-@pytest.mark.parametrize("cfg", ["6,32,5", "4,32,5", "4,32,3", "4,256,1"])
-def test_comparison_variants_stay_bit_exact(nb, golden_dir, cfg, monkeypatch):
-    """the kept comparison kernels (TMA/cp.async.bulk-staged, unsegmented warp-streaming, CTA-tiled)
-    compute the same bits as the production kernel and the reference"""
+@pytest.mark.parametrize("cfg", ["6,32,5", "4,32,5", "4,32,3", "4,256,1", "4,128,2"])
+def test_comparison_variants_stay_bit_exact(nb, vlib, golden_dir, cfg, monkeypatch):
+    """the comparison kernels of the VARIANTS library (TMA/cp.async.bulk-staged, unsegmented
+    warp-streaming, CTA-tiled packed and scalar) compute the same bits as the production kernel and
+    the reference; the product library refuses the ones it does not contain"""
     monkeypatch.setenv("NBODY_KERNEL_CONFIG", cfg)
     meta = json.load(open(os.path.join(golden_dir, "golden_meta.json")))
-    import oracle_lib
-    o = oracle_lib.Oracle()
-    sim = _mk(nb, 262144)
+    sim = _mk(nb, 262144, lib=vlib)
     if cfg.endswith(",1"):
         sim.setKernel(nb.KERNEL_PACKED)
-    assert o.fnv1a64(sim.computeAccel()) == meta["force"]["262144"]["fnv1a64"], sim.kernelName()
+    if cfg.endswith(",2"):
+        sim.setKernel(nb.KERNEL_SCALAR)
+    assert sha256_f32(sim.computeAccel()) == meta["force_sha256"]["262144"], sim.kernelName()
+    sim.stepSim()
+    sim.close()
+    if cfg.endswith(",1"):
+        prod = _mk(nb, 4096)
+        with pytest.raises(nb.NBodyError, match="VARIANTS"):
+            prod.setKernel(nb.KERNEL_PACKED)
+        prod.close()
+
+
+def test_many_launches_keep_ticket_and_epoch_numbering(nb, golden_dir, monkeypatch):
+    """hand-off words and the ticket counter run on across launches (and across kernels of different
+    group counts on one handle): 40 segmented launches, then the 10-step golden must still hold"""
+    monkeypatch.setenv("NBODY_SEGS", "5")
+    g = np.load(os.path.join(golden_dir, "step10_n2048.npz"))
+    sim = _mk(nb, 2048, simIterationsPerFrame=10)
+    init = _state(sim)
+    for _ in range(4):
+        sim.stepSim()
+    a1 = sim.computeAccel()
+    a2 = sim.computeAccel()
+    _assert_bits(a1, a2, "repeated accel pass")
+    sim.setState(*init)
+    sim.stepSim()
+    _assert_bits(_state(sim), [g[k] for k in ("x", "y", "z", "vx", "vy", "vz")], "golden after 40 earlier launches")
+    sim.close()
+
+
+def test_read_state_read_local_and_registered_host_memory(nb):
+    """nbody_read_state == read_pos + read_vel; nbody_read_local == the owned range of it; page-locked
+    (nbody_host_register) destination buffers give the same bits"""
+    import ctypes
+    n = 70000
+    sim = _mk(nb, n, simIterationsPerFrame=2)
+    sim.stepSim()
+    lib = nb.load_library()
+    sep = [np.empty(n, np.float32) for _ in range(6)]
+    nb._check(lib, lib.nbody_read_pos(sim._h, *[nb._ptr(a) for a in sep[:3]]), "read_pos")
+    nb._check(lib, lib.nbody_read_vel(sim._h, *[nb._ptr(a) for a in sep[3:]]), "read_vel")
+    one = [np.empty(n, np.float32) for _ in range(6)]
+    for a in one:
+        assert lib.nbody_host_register(a.ctypes.data_as(ctypes.c_void_p), a.nbytes) == 0, lib.nbody_last_error()
+    sim.readInto(*one)
+    _assert_bits(one, sep, "read_state into registered memory")
+    assert sim.localRange() == (0, n)
+    loc = [np.zeros(n, np.float32) for _ in range(6)]
+    sim.readLocalInto(*loc)
+    _assert_bits(loc, sep, "read_local")
+    for a in one:
+        assert lib.nbody_host_unregister(a.ctypes.data_as(ctypes.c_void_p)) == 0
     sim.close()
