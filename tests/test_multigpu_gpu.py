@@ -43,6 +43,35 @@ def test_sharded_step_bit_equal_to_single_gpu(nb, n, gpus, exchange, monkeypatch
     many.close()
 
 
+@pytest.mark.parametrize("gpus", [2, 4, 8])
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_sharded_forces_and_step_vs_reference_golden(nb, golden_dir, gpus, exchange, monkeypatch):
+    """pinned to the REFERENCE, not to this repo's single-GPU kernel: forces and one default step of the
+    sharded handle at N = 262144 (BASELINE configs[1]) against the SHA-256 of what the unmodified
+    reference kernel produced on a B200 (tests/golden/make_golden.py --big-only)"""
+    import hashlib
+    import json
+    import os
+    _need(nb, gpus)
+    monkeypatch.setenv("NBODY_EXCHANGE", exchange)
+    meta = json.load(open(os.path.join(golden_dir, "golden_meta.json")))
+    n = 262144
+
+    def sha(arrays):
+        return hashlib.sha256(np.stack(arrays, axis=1).reshape(-1).tobytes()).hexdigest()
+
+    many = nb.DiskGalaxySimulator(nb.SimParam(numParticles=n, simIterationsPerFrame=1), n_gpus=gpus)
+    assert sha(many.computeAccel()) == meta["force_sha256"][str(n)]
+    many.stepSim()
+    assert sha(_state(many)) == meta["step1_sha256"][str(n)]
+    b, c = many.localRange()
+    assert (b, c) == (0, n)
+    loc = [np.empty(n, np.float32) for _ in range(6)]
+    many.readLocalInto(*loc)
+    assert sha(loc) == meta["step1_sha256"][str(n)]
+    many.close()
+
+
 def test_sharded_generic_kernel_and_set_state(nb):
     _need(nb, 2)
     n = 5000
@@ -73,8 +102,26 @@ sim = nb.DiskGalaxySimulator(nb.SimParam(numParticles=n, simIterationsPerFrame=4
                              device=d.local_rank, unique_id=uid)
 sim.stepSim(); sim.stepSim()
 p, v = sim.getParticlePos(), sim.getParticleVel()
+full = [a.copy() for a in (p.x, p.y, p.z, v.x, v.y, v.z)]
+# a process-per-GPU application loop: upload state, step, read back only the bodies this rank owns.
+# No rank waits for the others between the calls (nbody_step itself is the only collective).
+b, c = sim.localRange()
+assert (b, c) == nb.plan_shard(n, d.world, d.rank)
+loc = [np.empty(c, np.float32) for _ in range(6)]
+cur = [a.copy() for a in full]
+for frame in range(3):
+    sim.setState(*cur)
+    sim.stepSim()
+    sim.readLocalInto(*loc)
+    # the full state for the next upload comes from the collective read
+    sim._host_fresh = False
+    p, v = sim.getParticlePos(), sim.getParticleVel()
+    cur = [a.copy() for a in (p.x, p.y, p.z, v.x, v.y, v.z)]
+    for k in range(6):
+        assert np.array_equal(loc[k], cur[k][b:b + c]), (frame, k)
 if d.rank == 0:
-    np.savez({out!r}, x=p.x, y=p.y, z=p.z, vx=v.x, vy=v.y, vz=v.z, name=sim.kernelName())
+    np.savez({out!r}, x=full[0], y=full[1], z=full[2], vx=full[3], vy=full[4], vz=full[5], name=sim.kernelName(),
+             x2=cur[0], vz2=cur[5])
 sim.close(); d.close()
 """
 
@@ -109,4 +156,9 @@ def test_one_process_per_gpu_matches_single_gpu(nb, tmp_path, exchange):
     one.stepSim(); one.stepSim()
     for a, k in zip(_state(one), ("x", "y", "z", "vx", "vy", "vz")):
         assert np.array_equal(a, g[k]), k
+    for _ in range(3):  # the upload / step / local read-back loop of the workers, on one GPU
+        one.setState(*_state(one))
+        one.stepSim()
+    st = _state(one)
+    assert np.array_equal(st[0], g["x2"]) and np.array_equal(st[5], g["vz2"])
     one.close()
