@@ -666,10 +666,15 @@ int nbody_set_kernel(nbody_handle *h, int kernel) {
   return 0;
 }
 
+// rewritten in the built library by tools/sass_sched.py with the number of kernels it re-scheduled
+extern "C" const volatile char nbody_sass_sched_marker[] = "NBODY_SASS_SCHED=00";
+
 const char *nbody_kernel_name(nbody_handle *h) {
   if (!h || h->devs.empty()) return "";
   char base[96];
   nbody::config_name(h->devs[0].cfg, base, sizeof base);
+  const bool sched = nbody_sass_sched_marker[17] != '0' || nbody_sass_sched_marker[18] != '0';
+  if (sched && h->devs[0].cfg.family == nbody::kFamSegmented) strncat(base, "+sass-sched", sizeof base - strlen(base) - 1);
   if (h->world > 1)
     snprintf(h->kname, sizeof h->kname, "%s|x%d:%s", base, h->world, h->exchange == 1 ? "peer-push" : "nccl-bcast");
   else
