@@ -25,6 +25,17 @@
 
 #include "nbody_body.cuh"
 
+// resident warps per SM promised to ptxas (= register budget) per register-blocking factor
+#ifndef NB_MINB2
+#define NB_MINB2 28
+#endif
+#ifndef NB_MINB4
+#define NB_MINB4 20
+#endif
+#ifndef NB_MINB6
+#define NB_MINB6 14
+#endif
+
 namespace nbody {
 
 // j-segmented launch.  A body group's sweep over j is cut into `segs` consecutive segments that are
@@ -291,10 +302,13 @@ cudaError_t launch_step(const KernelConfig &c, const StepArgs &a, cudaStream_t s
   }
   if (c.family == kFamSegmented || c.family == kFamUnsegmented) {
     const bool seg = c.family == kFamSegmented;
-    // (R, resident warps per SM promised to ptxas): the three tuned points, profiles/r01_tuning_log.txt
-    if (c.r == 2) return m ? launch_wseg<2, 28, true>(a, c.sms, seg, s) : launch_wseg<2, 28, false>(a, c.sms, seg, s);
-    if (c.r == 4) return m ? launch_wseg<4, 20, true>(a, c.sms, seg, s) : launch_wseg<4, 20, false>(a, c.sms, seg, s);
-    if (c.r == 6) return m ? launch_wseg<6, 14, true>(a, c.sms, seg, s) : launch_wseg<6, 14, false>(a, c.sms, seg, s);
+    // (R, resident warps per SM promised to ptxas): the tuned points, profiles/r01_tuning_log.txt and r02_sched_sweep.txt
+    if (c.r == 2) return m ? launch_wseg<2, NB_MINB2, true>(a, c.sms, seg, s) : launch_wseg<2, NB_MINB2, false>(a, c.sms, seg, s);
+    if (c.r == 4) return m ? launch_wseg<4, NB_MINB4, true>(a, c.sms, seg, s) : launch_wseg<4, NB_MINB4, false>(a, c.sms, seg, s);
+    if (c.r == 6) return m ? launch_wseg<6, NB_MINB6, true>(a, c.sms, seg, s) : launch_wseg<6, NB_MINB6, false>(a, c.sms, seg, s);
+#ifdef NB_MINB8
+    if (c.r == 8 && !m) return launch_wseg<8, NB_MINB8, false>(a, c.sms, seg, s);  // tuning builds only
+#endif
     return cudaErrorInvalidConfiguration;
   }
 #ifdef NBODY_VARIANTS
