@@ -162,16 +162,17 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
   int family = requested_kernel == 3 ? kFamScalarCta : (requested_kernel == 2 ? kFamPackedCta : kFamSegmented);
   int r = 4, block = 128;
   if (family == kFamSegmented) {
-    // one warp per CTA.  Wider register blocking (fewer LDS per interaction, more ILP, fewer
-    // resident warps) as long as the shard still supplies ~2 warps per resident slot:
-    // R = 6 at 14 warps/SM, R = 4 at 20, R = 2 at 28 (measured: profiles/r01_tuning_log.txt)
+    // one warp per CTA.  What decides is how many warps the shard yields: a single R = 6 warp nearly
+    // saturates its SM sub-partition (74 % of roofline asymptotically, R = 4: 72 %, R = 2: 69 %), but
+    // every one of the 4 x SMs sub-partitions needs work.  Measured switch points (profiles/r02_sched_sweep.txt):
+    //   >= ~281K bodies on 148 SMs : R = 6, 14 warps/SM
+    //   ~58K .. 281K               : R = 2, 28 warps/SM (R = 4 never wins once the tile body is post-scheduled)
+    //   below                      : scalar ops, one body per lane -- twice the warps of R = 2 again
+    //                                (the reference's interactive sizes; +44 % over packed R = 2 at N = 25 600)
     block = 32;
     r = 6;
-    if ((uint64_t)i_count < (uint64_t)sms * 2700u) r = 4;  // < ~400K bodies on 148 SMs
-    if ((uint64_t)i_count < (uint64_t)sms * 1350u) r = 2;  // < ~200K bodies
-    if ((uint64_t)i_count <= (uint64_t)sms * 128u) {
-      // at most one warp per SM sub-partition even at one body per lane (the reference's interactive
-      // sizes, N <= ~19K): scalar ops, R = 1 -- 1.5x the packed kernel there
+    if ((uint64_t)i_count < (uint64_t)sms * 1900u) r = 2;
+    if ((uint64_t)i_count <= (uint64_t)sms * 390u) {
       family = kFamSmall;
       r = 1;
     }
@@ -234,7 +235,7 @@ uint32_t plan_segments(uint32_t groups, uint32_t nj, int sms, int k_max) {
     if (v >= 1 && v <= 1024) return (uint32_t)v;
   }
   const double gens = (double)groups / ((double)sms * k_max);
-  if (gens < 0.25) return 1;  // far fewer warps than slots: later segments would only spin (measured, N < 64K)
+  if (gens < 0.4) return 1;  // far fewer warps than slots: later segments would only spin (measured, N < ~100K at R = 2)
   int segs = (int)ceil(16.0 / (gens > 0.05 ? gens : 0.05));
   if (segs > 64) segs = 64;
   while (segs > 1 && nj / segs < 4096) segs--;  // keep segments long: hand-off cost stays invisible

@@ -518,13 +518,18 @@ def test_checkpoint_resume_is_bit_identical(nb, tmp_path):
     c.close()
 
 
-@pytest.mark.parametrize("n", [200001, 400003])
-def test_register_blocking_switch_points_ragged(nb, ref, n):
-    """sizes just past the R = 2 -> 4 -> 6 switch points, not a multiple of anything: exercises the
-    ragged last group of the R = 4 / R = 6 segmented kernels against the reference kernel"""
+@pytest.mark.parametrize("n,cfg", [(57001, "wsmall_scalar_r1"), (58003, "wseg_f32x2_r2"), (200001, "wseg_f32x2_r2"),
+                                   (281003, "wseg_f32x2_r2"), (281303, "wseg_f32x2_r6"), (400003, "wseg_f32x2_r6"),
+                                   (200001, "4,32,4")])
+def test_register_blocking_switch_points_ragged(nb, ref, n, cfg, monkeypatch):
+    """sizes on both sides of the scalar -> R = 2 -> R = 6 switch points, not a multiple of anything:
+    exercises the ragged last group of every AUTO kernel (and of the R = 4 instantiation, which AUTO no
+    longer picks) against the reference kernel"""
+    if "," in cfg:
+        monkeypatch.setenv("NBODY_KERNEL_CONFIG", cfg)
     fx, fy, fz, _ = ref.reference_forces(n)
     sim = _mk(nb, n)
-    assert ("_r4_" if n < 399000 else "_r6_") in sim.kernelName()
+    assert (cfg if "," not in cfg else "wseg_f32x2_r4") in sim.kernelName(), sim.kernelName()
     _assert_bits(sim.computeAccel(), [fx, fy, fz], f"forces N={n}")
     sim.close()
 

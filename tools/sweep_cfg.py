@@ -13,7 +13,8 @@ segs = [int(x) for x in sys.argv[3].split(",")]
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 for r in rs:
     for sg in segs:
-        os.environ["NBODY_KERNEL_CONFIG"] = f"{r},32,4"
+        fam = int(os.environ.get("SWEEP_FAMILY", "4"))
+        os.environ["NBODY_KERNEL_CONFIG"] = f"{r},32,{fam}"
         if sg: os.environ["NBODY_SEGS"] = str(sg)
         else: os.environ.pop("NBODY_SEGS", None)
         sim = nb.DiskGalaxySimulator(nb.SimParam(numParticles=n, simIterationsPerFrame=1))
