@@ -176,7 +176,8 @@ __device__ __forceinline__ void finish_body(const StepArgs &a, const int flags, 
 // (not by blockIdx), so the predecessor -- which holds a smaller ticket -- is by construction
 // already running or finished, whatever order the hardware dispatches CTAs in: forward progress
 // does not depend on dispatch order (the decoupled look-back construction).  A legitimate wait is
-// at most one unit long.  If a wait nevertheless exceeds ~20 s (debugger, time-slicing) the kernel
+// at most one unit long.  If a wait nevertheless exceeds the time-out (20 s by default; debugger,
+// time-slicing, a sanitizer slowing the kernel 1000x: NBODY_HANDOFF_TIMEOUT_S, 0 = never) the kernel
 // raises the host-visible error word and carries on -- nbody_step() then reports NBODY_E_STATE
 // instead of the context being torn down by a trap.
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -185,14 +186,15 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-__device__ __forceinline__ void wait_for_segment(unsigned int *word, unsigned int target, unsigned int *error) {
+__device__ __forceinline__ void wait_for_segment(unsigned int *word, unsigned int target, unsigned int *error,
+                                                 const unsigned long long timeout_ns) {
   volatile unsigned int *p = word;
   if (*p != target) {
     const unsigned long long t0 = global_ns();
     unsigned int spins = 0;
     while (*p != target) {
       __nanosleep(128);
-      if ((++spins & 0x3fffu) == 0 && global_ns() - t0 > 20000000000ull) {
+      if ((++spins & 0x3fffu) == 0 && timeout_ns && global_ns() - t0 > timeout_ns) {
         *(volatile unsigned int *)error = 1u;
         __threadfence_system();
         break;

@@ -186,6 +186,7 @@ int alloc_device(nbody_handle *h, DeviceCtx &d) {
   d.sync.n_groups = (uint32_t)(own / 64 + 2);
   CK(cudaMalloc(&d.sync.words, ((size_t)d.sync.n_groups + 1) * sizeof(unsigned int)));
   CK(cudaMemset(d.sync.words, 0, ((size_t)d.sync.n_groups + 1) * sizeof(unsigned int)));
+  if (const char *e = getenv("NBODY_HANDOFF_TIMEOUT_S")) d.sync.timeout_ns = (unsigned long long)(atof(e) * 1e9);
   CK(cudaHostAlloc(&d.error_host, sizeof(unsigned int), cudaHostAllocMapped));
   *d.error_host = 0;
   CK(cudaHostGetDevicePointer(&d.sync.error, d.error_host, 0));
@@ -805,9 +806,10 @@ int nbody_step(nbody_handle *h) {
   for (auto &d : h->devs)
     if (d.error_host && *(volatile unsigned int *)d.error_host) {
       *d.error_host = 0;
-      return fail(NBODY_E_STATE, "device %d: a j-segment hand-off wait exceeded 20 s (GPU time-sliced or halted by a "
-                                 "debugger?); the state of this handle is no longer valid -- reload it with nbody_set_state",
-                  d.device);
+      return fail(NBODY_E_STATE, "device %d: a j-segment hand-off wait exceeded %.0f s (GPU time-sliced, halted by a debugger or "
+                                 "slowed by a sanitizer? NBODY_HANDOFF_TIMEOUT_S=0 waits for ever); the state of this handle is no "
+                                 "longer valid -- reload it with nbody_set_state",
+                  d.device, d.sync.timeout_ns * 1e-9);
     }
   return 0;
 }

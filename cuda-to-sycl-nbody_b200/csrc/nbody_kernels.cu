@@ -51,7 +51,7 @@ template <int R, int MINB, bool MASS>
 __global__ void __launch_bounds__(32, MINB)
     force_wseg_kernel(const StepArgs a, const uint32_t groups, const uint32_t segs, const uint32_t seg_len,
                       unsigned int *words, unsigned int *error, const unsigned int epoch,
-                      const unsigned int ticket_base) {
+                      const unsigned int ticket_base, const unsigned long long timeout_ns) {
   __shared__ __align__(16) float4 s_tile[2][32];
   const int lane = threadIdx.x & 31;
   uint32_t unit = blockIdx.x;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(32, MINB)
   const uint32_t j_end = min(a.j_end, j_begin + seg_len);
   const int flags = (seg == 0 ? (a.flags & kFirstChunk) : 0) | (seg == segs - 1 ? (a.flags & (kLastChunk | kAccelOut)) : 0);
   if (seg > 0) {
-    if (lane == 0) wait_for_segment(words + 1 + g, epoch + seg, error);
+    if (lane == 0) wait_for_segment(words + 1 + g, epoch + seg, error, timeout_ns);
     __syncwarp();
   }
   warp_sweep_packed<R, MASS>(a, j_begin, j_end, flags, warp_i, s_tile, lane);
@@ -270,7 +270,7 @@ static cudaError_t launch_wseg(const StepArgs &a, int sms, bool segmented, cudaS
     sy->ticket_base += groups * segs;  // wraps with the device counter (unsigned arithmetic on both sides)
   }
   force_wseg_kernel<R, MINB, MASS><<<groups * segs, 32, 0, s>>>(a, groups, segs, seg_len, sy ? sy->words : nullptr,
-                                                                sy ? sy->error : nullptr, ep, tb);
+                                                                sy ? sy->error : nullptr, ep, tb, sy ? sy->timeout_ns : 0ull);
   e = cudaGetLastError();
   if (e != cudaSuccess && segs > 1) {  // nothing ran: keep host and device numbering in step
     sy->epoch -= segs;

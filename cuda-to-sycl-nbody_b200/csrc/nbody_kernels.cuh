@@ -26,6 +26,7 @@ struct SegSync {
   uint32_t n_groups = 0;          // hand-off words available
   unsigned int epoch = 0;         // running segment counter: hand-off words are compared against epoch + seg
   unsigned int ticket_base = 0;   // value of the ticket counter when the next launch starts
+  unsigned long long timeout_ns = 20000000000ull;  // hand-off wait time-out (0 = wait for ever)
 };
 
 struct StepArgs {

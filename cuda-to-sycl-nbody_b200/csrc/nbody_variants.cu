@@ -138,7 +138,7 @@ template <int R, int MINB>
 __global__ void __launch_bounds__(32, MINB)
     force_wseg_tma_kernel(const StepArgs a, const uint32_t groups, const uint32_t segs, const uint32_t seg_len,
                           unsigned int *words, unsigned int *error, const unsigned int epoch,
-                          const unsigned int ticket_base) {
+                          const unsigned int ticket_base, const unsigned long long timeout_ns) {
   static_assert(R % 2 == 0, "packed kernel pairs i-bodies");
   constexpr int NP = R / 2;
   constexpr int TJ = 32;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(32, MINB)
     nz[p] = pack2(-own[2 * p].z, -own[2 * p + 1].z);
   }
   if (seg > 0) {
-    if (lane == 0) wait_for_segment(words + 1 + g, epoch + seg, error);
+    if (lane == 0) wait_for_segment(words + 1 + g, epoch + seg, error, timeout_ns);
     __syncwarp();
   }
 #pragma unroll
@@ -274,7 +274,7 @@ static cudaError_t launch_wseg_tma(const StepArgs &a, int sms, cudaStream_t s) {
     sy->ticket_base += groups * segs;
   }
   force_wseg_tma_kernel<R, MINB><<<groups * segs, 32, 0, s>>>(a, groups, segs, seg_len, sy ? sy->words : nullptr,
-                                                              sy ? sy->error : nullptr, ep, tb);
+                                                              sy ? sy->error : nullptr, ep, tb, sy ? sy->timeout_ns : 0ull);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess && segs > 1) {
     sy->epoch -= segs;

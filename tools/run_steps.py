@@ -24,13 +24,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--iters", type=int, default=1)
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--resident", type=int, default=0, help="NBODY_RESIDENT_CTAS override")
+    ap.add_argument("--segs", type=int, default=0, help="NBODY_SEGS override")
+    ap.add_argument("--variants", action="store_true", help="load libnbody_b200_variants.so (comparison kernels)")
     a = ap.parse_args()
     if a.cfg:
         os.environ["NBODY_KERNEL_CONFIG"] = a.cfg
-    if a.resident:
-        os.environ["NBODY_RESIDENT_CTAS"] = str(a.resident)
-    sim = nb.DiskGalaxySimulator(nb.SimParam(numParticles=a.n, simIterationsPerFrame=a.iters), n_gpus=a.gpus)
+    if a.segs:
+        os.environ["NBODY_SEGS"] = str(a.segs)
+    lib = nb.load_library(nb.VARIANTS_LIB_PATH) if a.variants or a.kernel in ("packed", "scalar") else None
+    sim = nb.DiskGalaxySimulator(nb.SimParam(numParticles=a.n, simIterationsPerFrame=a.iters), n_gpus=a.gpus, lib=lib)
     sim.setKernel(KERNELS[a.kernel])
     for s in range(a.steps):
         sim.stepSim()
