@@ -54,6 +54,10 @@ __global__ void __launch_bounds__(32, MINB)
                       const unsigned int ticket_base, const unsigned long long timeout_ns) {
   __shared__ __align__(16) float4 s_tile[2][32];
   const int lane = threadIdx.x & 31;
+#ifdef NB_SMEM_PAD  // tuning builds only (tools/sass_lab.py): extra static shared memory caps the resident warps per SM
+  __shared__ float s_pad[NB_SMEM_PAD / 4];
+  if (a.n == 0xffffffffu) ((volatile float *)s_pad)[lane] = 0.0f;
+#endif
   uint32_t unit = blockIdx.x;
   if (segs > 1) {  // take a ticket: units are numbered in the order CTAs actually start
     unsigned int t = 0;
