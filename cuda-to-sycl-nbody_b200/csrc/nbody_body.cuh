@@ -215,11 +215,37 @@ __device__ __forceinline__ void sweep_warp_tiles(const float4 *__restrict__ pos,
   constexpr int TJ = 32;
   const uint32_t nj = j_end - j_begin;
   const uint32_t ntiles = (nj + TJ - 1) / TJ;
+  if (ntiles == 0) return;
+#ifndef NB_LOOP_BRANCHY
+  // The per-tile bookkeeping competes with the arithmetic for issue slots (every instruction costs the
+  // sub-partition at least one issue cycle, tools/sass_lab.py), so it is kept branch-free: the next tile is
+  // always fetched (index clamped to the last j-body, a harmless re-read behind the last tile) and always
+  // stored (behind the last tile nobody reads it).
+  const uint32_t last = j_end - 1;
+  uint32_t jn = j_begin + lane;
+  tile[0][lane] = pos[min(jn, last)];
+  __syncwarp();
+  for (uint32_t t = 0; t < ntiles; t++) {
+    const int buf = t & 1;
+    jn += TJ;
+    const float4 nxt = pos[min(jn, last)];
+    const uint32_t cnt = min((uint32_t)TJ, nj - t * TJ);
+    const uint32_t gj0 = j_begin + t * TJ;
+    if (cnt == TJ) {
+#pragma unroll
+      for (int j = 0; j < TJ; j++) body(tile[buf][j], gj0 + j);
+    } else {
+      for (uint32_t j = 0; j < cnt; j++) body(tile[buf][j], gj0 + j);
+    }
+    tile[buf ^ 1][lane] = nxt;
+    __syncwarp();
+  }
+#else
   auto fetch = [&](uint32_t t) -> float4 {
     uint32_t j = j_begin + t * TJ + lane;
     return pos[j < j_end ? j : j_end - 1];
   };
-  if (ntiles > 0) tile[0][lane] = fetch(0);
+  tile[0][lane] = fetch(0);
   __syncwarp();
   for (uint32_t t = 0; t < ntiles; t++) {
     const int buf = t & 1;
@@ -237,6 +263,7 @@ __device__ __forceinline__ void sweep_warp_tiles(const float4 *__restrict__ pos,
     if (more) tile[buf ^ 1][lane] = nxt;
     __syncwarp();
   }
+#endif
 }
 
 // one warp's packed sweep: R*32 i-bodies starting at shard-local index warp_i against j in [j_begin, j_end)
