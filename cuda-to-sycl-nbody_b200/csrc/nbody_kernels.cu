@@ -25,15 +25,39 @@
 
 #include "nbody_body.cuh"
 
-// resident warps per SM promised to ptxas (= register budget) per register-blocking factor
+// Resident warps per SM promised to ptxas (= register budget) per register-blocking factor.  The unrolled tile
+// body is regenerated after linking (tools/sass_gen.py) with its own register allocation: double-buffered
+// differences and weights need ~44 registers next to the negated positions and accumulators, so every
+// instantiation gets a 128-register budget (16 resident warps per SM; the generated single-warp schedule keeps a
+// sub-partition's issue port busy with 3-4 warps, profiles/r02_sched_sweep.txt).
 #ifndef NB_MINB2
-#define NB_MINB2 28
+#define NB_MINB2 16
 #endif
 #ifndef NB_MINB4
-#define NB_MINB4 20
+#define NB_MINB4 16
 #endif
 #ifndef NB_MINB6
 #define NB_MINB6 14
+#endif
+// the per-body-mass instantiations keep ptxas' instructions (re-ordered by tools/sass_sched.py): the budgets they were tuned at
+#ifndef NB_MINB2M
+#define NB_MINB2M 28
+#endif
+#ifndef NB_MINB4M
+#define NB_MINB4M 20
+#endif
+#ifndef NB_MINB6M
+#define NB_MINB6M 14
+#endif
+// AUTO switch points in bodies per SM (see choose_config)
+#ifndef NB_SW6
+#define NB_SW6 2304u
+#endif
+#ifndef NB_SW4
+#define NB_SW4 1536u
+#endif
+#ifndef NB_SW2
+#define NB_SW2 390u
 #endif
 
 namespace nbody {
@@ -166,17 +190,21 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
   int family = requested_kernel == 3 ? kFamScalarCta : (requested_kernel == 2 ? kFamPackedCta : kFamSegmented);
   int r = 4, block = 128;
   if (family == kFamSegmented) {
-    // one warp per CTA.  What decides is how many warps the shard yields: a single R = 6 warp nearly
-    // saturates its SM sub-partition (74 % of roofline asymptotically, R = 4: 72 %, R = 2: 69 %), but
-    // every one of the 4 x SMs sub-partitions needs work.  Measured switch points (profiles/r02_sched_sweep.txt):
-    //   >= ~281K bodies on 148 SMs : R = 6, 14 warps/SM
-    //   ~58K .. 281K               : R = 2, 28 warps/SM (R = 4 never wins once the tile body is post-scheduled)
-    //   below                      : scalar ops, one body per lane -- twice the warps of R = 2 again
-    //                                (the reference's interactive sizes; +44 % over packed R = 2 at N = 25 600)
+    // one warp per CTA.  What decides is how many warps the shard yields: with the generated tile body a warp's
+    // cost per pair-interaction hardly depends on R (26.1 cycles at R = 6, 26.7 at R = 4, 27.9 at R = 2: the
+    // LDS.128 and the tile bookkeeping are shared by R/2 pairs), but every one of the 4 x SMs sub-partitions
+    // needs about three warps for the hand-off segments to balance.  Measured switch points on 148 SMs
+    // (profiles/r02_sched_sweep.txt):
+    //   >= ~NB_SW6 bodies per SM : R = 6          (76.7 % of the FP32 roofline at N = 1M)
+    //   >= ~NB_SW4               : R = 4          (74.8 % at N = 262 144)
+    //   >= ~NB_SW2               : R = 2          (71.8 % at N = 131 072)
+    //   below                    : scalar ops, one body per lane -- twice the warps of R = 2 again
+    //                              (the reference's interactive sizes)
     block = 32;
     r = 6;
-    if ((uint64_t)i_count < (uint64_t)sms * 1900u) r = 2;
-    if ((uint64_t)i_count <= (uint64_t)sms * 390u) {
+    if ((uint64_t)i_count < (uint64_t)sms * NB_SW6) r = 4;
+    if ((uint64_t)i_count < (uint64_t)sms * NB_SW4) r = 2;
+    if ((uint64_t)i_count <= (uint64_t)sms * NB_SW2) {
       family = kFamSmall;
       r = 1;
     }
@@ -308,9 +336,9 @@ cudaError_t launch_step(const KernelConfig &c, const StepArgs &a, cudaStream_t s
   if (c.family == kFamSegmented || c.family == kFamUnsegmented) {
     const bool seg = c.family == kFamSegmented;
     // (R, resident warps per SM promised to ptxas): the tuned points, profiles/r01_tuning_log.txt and r02_sched_sweep.txt
-    if (c.r == 2) return m ? launch_wseg<2, NB_MINB2, true>(a, c.sms, seg, s) : launch_wseg<2, NB_MINB2, false>(a, c.sms, seg, s);
-    if (c.r == 4) return m ? launch_wseg<4, NB_MINB4, true>(a, c.sms, seg, s) : launch_wseg<4, NB_MINB4, false>(a, c.sms, seg, s);
-    if (c.r == 6) return m ? launch_wseg<6, NB_MINB6, true>(a, c.sms, seg, s) : launch_wseg<6, NB_MINB6, false>(a, c.sms, seg, s);
+    if (c.r == 2) return m ? launch_wseg<2, NB_MINB2M, true>(a, c.sms, seg, s) : launch_wseg<2, NB_MINB2, false>(a, c.sms, seg, s);
+    if (c.r == 4) return m ? launch_wseg<4, NB_MINB4M, true>(a, c.sms, seg, s) : launch_wseg<4, NB_MINB4, false>(a, c.sms, seg, s);
+    if (c.r == 6) return m ? launch_wseg<6, NB_MINB6M, true>(a, c.sms, seg, s) : launch_wseg<6, NB_MINB6, false>(a, c.sms, seg, s);
 #ifdef NB_MINB8
     if (c.r == 8 && !m) return launch_wseg<8, NB_MINB8, false>(a, c.sms, seg, s);  // tuning builds only
 #endif

@@ -322,7 +322,7 @@ def test_full_size_forces_and_step_vs_reference_golden(nb, golden_dir):
     meta = json.load(open(os.path.join(golden_dir, "golden_meta.json")))
     n = 1048576
     sim = _mk(nb, n, simIterationsPerFrame=1)
-    assert "wseg_f32x2_r6" in sim.kernelName()
+    assert "wseg_f32x2_r6" in sim.kernelName() and "+sass-gen" in sim.kernelName(), sim.kernelName()
     a = sim.computeAccel()
     assert sha256_f32(a) == meta["force_sha256"][str(n)]
     for c in a:
@@ -335,7 +335,7 @@ def test_full_size_forces_and_step_vs_reference_golden(nb, golden_dir):
 
 @pytest.mark.parametrize("n", [262144, 400003])
 def test_mid_size_forces_vs_reference_golden(nb, golden_dir, n):
-    """configs[1] (262144, R = 4 kernel) and a ragged size just above the R = 6 switch point"""
+    """configs[1] (262144, R = 4 kernel) and a ragged size above the R = 6 switch point"""
     meta = json.load(open(os.path.join(golden_dir, "golden_meta.json")))
     sim = _mk(nb, n, simIterationsPerFrame=1)
     assert sha256_f32(sim.computeAccel()) == meta["force_sha256"][str(n)]
@@ -518,19 +518,34 @@ def test_checkpoint_resume_is_bit_identical(nb, tmp_path):
     c.close()
 
 
-@pytest.mark.parametrize("n,cfg", [(57001, "wsmall_scalar_r1"), (58003, "wseg_f32x2_r2"), (200001, "wseg_f32x2_r2"),
-                                   (281003, "wseg_f32x2_r2"), (281303, "wseg_f32x2_r6"), (400003, "wseg_f32x2_r6"),
-                                   (200001, "4,32,4")])
+@pytest.mark.parametrize("n,cfg", [(57001, None), (58003, None), (113003, None), (200001, None), (227003, None),
+                                   (281303, None), (341003, None), (400003, None),
+                                   (58003, "2,32,4"), (200001, "4,32,4"), (200001, "6,32,4"), (400003, "2,32,4"),
+                                   (400003, "4,32,4"), (131072, "6,32,4")])
 def test_register_blocking_switch_points_ragged(nb, ref, n, cfg, monkeypatch):
-    """sizes on both sides of the scalar -> R = 2 -> R = 6 switch points, not a multiple of anything:
-    exercises the ragged last group of every AUTO kernel (and of the R = 4 instantiation, which AUTO no
-    longer picks) against the reference kernel"""
-    if "," in cfg:
+    """ragged sizes (not a multiple of anything) around the scalar -> R = 2 -> R = 4 -> R = 6 switch points of AUTO,
+    and every register-blocking factor forced at sizes AUTO would not use it for: exercises the ragged last group
+    and the generated tile body (tools/sass_gen.py) of every instantiation against the reference kernel"""
+    if cfg:
         monkeypatch.setenv("NBODY_KERNEL_CONFIG", cfg)
     fx, fy, fz, _ = ref.reference_forces(n)
     sim = _mk(nb, n)
-    assert (cfg if "," not in cfg else "wseg_f32x2_r4") in sim.kernelName(), sim.kernelName()
-    _assert_bits(sim.computeAccel(), [fx, fy, fz], f"forces N={n}")
+    name = sim.kernelName()
+    if cfg:
+        assert f"wseg_f32x2_r{cfg[0]}" in name, name
+    else:
+        assert "wseg_f32x2_r" in name or "wsmall_scalar_r1" in name, name
+    _assert_bits(sim.computeAccel(), [fx, fy, fz], f"forces N={n} ({name})")
+    sim.close()
+
+
+def test_post_link_step_is_reported(nb):
+    """the library says what the post-link step did to the kernel it runs: the unit-mass production kernels carry a
+    generated tile body (+sass-gen), the per-body-mass ones ptxas' instructions in a better order (+sass-sched)"""
+    sim = _mk(nb, 400003)
+    assert sim.kernelName().endswith("+sass-gen"), sim.kernelName()
+    sim.setMass(np.full(400003, 1.0, np.float32))
+    assert "+sass-gen" not in sim.kernelName(), sim.kernelName()
     sim.close()
 
 

@@ -560,7 +560,7 @@ def add_options(ap):
     ap.add_argument("--extra-buf", type=int, default=0, help="additional difference/weight buffers per slot")
     ap.add_argument("--quads", type=int, default=2, help="LDS.128 destination buffers")
     ap.add_argument("--lds-ahead", type=int, default=1, help="periods between an LDS and the first use of its tile word")
-    ap.add_argument("--mufu-gap", type=int, default=8, help="minimum cycles between two MUFUs of the warp")
+    ap.add_argument("--mufu-gap", type=int, default=10, help="minimum cycles between two MUFUs of the warp")
     ap.add_argument("--no-mufu-between", dest="mufu_between", action="store_false",
                     help="no MUFU in the shadow of the last accumulate of a triplet")
     ap.add_argument("--tri-order", default="0,1,2", type=lambda s: tuple(int(v) for v in s.split(",")))
