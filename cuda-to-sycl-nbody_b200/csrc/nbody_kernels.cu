@@ -2,7 +2,7 @@
 // their host-side dispatch.  The arithmetic lives in nbody_body.cuh (one definition of the packed
 // 12-op body, one of the scalar body, shared by every kernel); this file decides how it is fed:
 //
-//   * force_wseg_kernel<R, MINB, MASS>  (AUTO for shards above ~19K bodies)
+//   * force_wseg_kernel<R, MINB, MASS>  (AUTO: R = 6 / 4 / 2 by shard size, see choose_config)
 //     one warp per CTA, R i-bodies per lane in f32x2 pairs, warp-private 32-body j-tiles (LDG.128 ->
 //     STS.128 -> __syncwarp -> broadcast LDS.128, double buffered, no CTA barrier), and the j-sweep
 //     of a body group cut into consecutive work units of ONE grid that hand the accumulators on
@@ -51,13 +51,10 @@
 #endif
 // AUTO switch points in bodies per SM (see choose_config)
 #ifndef NB_SW6
-#define NB_SW6 2304u
+#define NB_SW6 3100u
 #endif
 #ifndef NB_SW4
-#define NB_SW4 1536u
-#endif
-#ifndef NB_SW2
-#define NB_SW2 390u
+#define NB_SW4 1650u
 #endif
 
 namespace nbody {
@@ -191,22 +188,43 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
   int r = 4, block = 128;
   if (family == kFamSegmented) {
     // one warp per CTA.  What decides is how many warps the shard yields: with the generated tile body a warp's
-    // cost per pair-interaction hardly depends on R (26.1 cycles at R = 6, 26.7 at R = 4, 27.9 at R = 2: the
+    // cost per pair-interaction hardly depends on R (26.1 cycles at R = 6, 26.2 at R = 4, 27.0 at R = 2: the
     // LDS.128 and the tile bookkeeping are shared by R/2 pairs), but every one of the 4 x SMs sub-partitions
-    // needs about three warps for the hand-off segments to balance.  Measured switch points on 148 SMs
-    // (profiles/r02_sched_sweep.txt):
-    //   >= ~NB_SW6 bodies per SM : R = 6          (76.7 % of the FP32 roofline at N = 1M)
-    //   >= ~NB_SW4               : R = 4          (74.8 % at N = 262 144)
-    //   >= ~NB_SW2               : R = 2          (71.8 % at N = 131 072)
-    //   below                    : scalar ops, one body per lane -- twice the warps of R = 2 again
-    //                              (the reference's interactive sizes)
+    // needs about three warps before the hand-off segments balance the machine.  Measured on 148 SMs
+    // (profiles/r02_sched_sweep.txt, section 3):
+    //   >= NB_SW6 bodies per SM (459K) : R = 6     76.7 % of the FP32 roofline at N = 1M
+    //   >= NB_SW4 (244K)               : R = 4     74.8 % at N = 262 144, 76.3 % at 400 003
+    //   >= 768 (114K)                  : R = 2     71.7 % at N = 131 072
+    //   below: the sub-partitions hold 0-2 warps each and the quantisation decides -- pick the cheapest of
+    //   {scalar one-body-per-lane, R = 2, R = 4} by  ceil(warps / sub-partitions) x bodies per warp / efficiency
+    //   of a sub-partition holding that many warps of that kind (table below, from the same sweep).
     block = 32;
     r = 6;
     if ((uint64_t)i_count < (uint64_t)sms * NB_SW6) r = 4;
     if ((uint64_t)i_count < (uint64_t)sms * NB_SW4) r = 2;
-    if ((uint64_t)i_count <= (uint64_t)sms * NB_SW2) {
-      family = kFamSmall;
-      r = 1;
+    if ((uint64_t)i_count < (uint64_t)sms * 768u) {
+      static const double eff[3][4] = {{0.376, 0.47, 0.53, 0.57},   // scalar, 1 / 2 / 3 / >= 4 warps per sub-partition
+                                       {0.58, 0.66, 0.72, 0.74},    // R = 2
+                                       {0.68, 0.74, 0.755, 0.763}}; // R = 4
+      static const int bodies[3] = {32, 64, 128};
+      const uint64_t smsp = 4ull * (uint64_t)sms;
+      double best = 0.0;
+      int pick = 0;
+      for (int k = 0; k < 3; k++) {
+        const uint64_t warps = ((uint64_t)i_count + bodies[k] - 1) / bodies[k];
+        const uint64_t w = (warps + smsp - 1) / smsp;
+        const double cost = (double)w * bodies[k] / eff[k][w >= 4 ? 3 : (w < 1 ? 0 : w - 1)];
+        if (k == 0 || cost < best * 0.999) {
+          best = cost;
+          pick = k;
+        }
+      }
+      if (pick == 0) {
+        family = kFamSmall;
+        r = 1;
+      } else {
+        r = pick == 1 ? 2 : 4;
+      }
     }
   } else {
     // CTA-tiled comparison kernels: i-bodies per CTA = block*r; keep ~4 CTA-tiles per SM

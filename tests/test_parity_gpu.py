@@ -518,8 +518,9 @@ def test_checkpoint_resume_is_bit_identical(nb, tmp_path):
     c.close()
 
 
-@pytest.mark.parametrize("n,cfg", [(57001, None), (58003, None), (113003, None), (200001, None), (227003, None),
-                                   (281303, None), (341003, None), (400003, None),
+@pytest.mark.parametrize("n,cfg", [(32003, None), (40003, None), (57001, None), (65003, None), (113003, None),
+                                   (114003, None), (200001, None), (244003, None), (244403, None), (400003, None),
+                                   (458003, None), (459003, None),
                                    (58003, "2,32,4"), (200001, "4,32,4"), (200001, "6,32,4"), (400003, "2,32,4"),
                                    (400003, "4,32,4"), (131072, "6,32,4")])
 def test_register_blocking_switch_points_ragged(nb, ref, n, cfg, monkeypatch):
