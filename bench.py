@@ -449,11 +449,12 @@ def run_b200_arm(args, dist, emit):
     roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": traffic_for(n_gpus, n),
                 "peak_source": f"148 SMs x 128 FP32 lanes x 2 flop x sm_max_mhz of MEASURED_PEAKS.json ({peak_src})",
-                "convention": "20 flop/interaction (north_star); the exact 12-op recipe is FMA-pipe bound at 83.3% of this",
+                "convention": "20 flop/interaction (north_star); the exact 12-op recipe + 1 MUFU per interaction is issue bound at "
+                              "~76.9% of this (24 + 2 issue cycles per 64 interactions per SM sub-partition, profiles/r02_sass_lab.txt)",
                 "per_gpu": True,
                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": peaks.get("hbm_gbs"), "frac": hbm_gbs / peaks.get("hbm_gbs", 6448.4),
                         "algorithmic_bytes_per_step_per_gpu": alg_bytes},
-                "note": "path is FP32-FMA-pipe / register-file bound, neither HBM nor tensor: see DESIGN.md section 5; "
+                "note": "path is bound by the FP32 issue port, neither HBM nor tensor: see DESIGN.md section 5; "
                         "traffic = dram bytes per launch from the ncu capture of THIS config (profiles/r02_traffic.json) or null"}
 
     if args.weak_base:
