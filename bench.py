@@ -452,6 +452,9 @@ def run_b200_arm(args, dist, emit):
                 "convention": "20 flop/interaction (north_star); the exact 12-op recipe + 1 MUFU per interaction is issue bound at "
                               "~76.9% of this (24 + 2 issue cycles per 64 interactions per SM sub-partition, profiles/r02_sass_lab.txt)",
                 "per_gpu": True,
+                # the practical ceiling of the exact recipe on this chip: per 64 interactions a sub-partition's issue port is
+                # held 24 cycles by the 12 packed ops and 2 by the MUFUs (profiles/r02_sass_lab.txt) vs 20 at the 20-flop roofline
+                "issue_bound": {"frac_of_roofline": 20.0 / 26.0, "achieved_frac_of_issue_bound": (achieved_tf / peak_tf) / (20.0 / 26.0)},
                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": peaks.get("hbm_gbs"), "frac": hbm_gbs / peaks.get("hbm_gbs", 6448.4),
                         "algorithmic_bytes_per_step_per_gpu": alg_bytes},
                 "note": "path is bound by the FP32 issue port, neither HBM nor tensor: see DESIGN.md section 5; "

@@ -671,6 +671,7 @@ int nbody_set_kernel(nbody_handle *h, int kernel) {
 // unrolled tile body it re-ordered (sass_sched.py) / regenerated from scratch (sass_gen.py)
 extern "C" const volatile char nbody_sass_sched_marker[] = "NBODY_SASS_SCHED=00";
 extern "C" const volatile char nbody_sass_gen_marker[] = "NBODY_SASS_GEN=00";
+extern "C" const volatile char nbody_sass_genm_marker[] = "NBODY_SASS_GENM=00";  // ... of the per-body-mass instantiations
 
 const char *nbody_kernel_name(nbody_handle *h) {
   if (!h || h->devs.empty()) return "";
@@ -678,11 +679,11 @@ const char *nbody_kernel_name(nbody_handle *h) {
   nbody::config_name(h->devs[0].cfg, base, sizeof base);
   const bool sched = nbody_sass_sched_marker[17] != '0' || nbody_sass_sched_marker[18] != '0';
   const bool gen = nbody_sass_gen_marker[15] != '0' || nbody_sass_gen_marker[16] != '0';
+  const bool genm = nbody_sass_genm_marker[16] != '0' || nbody_sass_genm_marker[17] != '0';
   const nbody::KernelConfig &kc = h->devs[0].cfg;
   if (kc.family == nbody::kFamSegmented || kc.family == nbody::kFamUnsegmented) {
-    // unit-mass instantiations are regenerated when the generator ran; the per-body-mass ones are re-ordered
-    if (gen && !kc.mass) strncat(base, "+sass-gen", sizeof base - strlen(base) - 1);
-    else if (sched || gen) strncat(base, "+sass-sched", sizeof base - strlen(base) - 1);
+    if (kc.mass ? genm : gen) strncat(base, "+sass-gen", sizeof base - strlen(base) - 1);
+    else if (sched) strncat(base, "+sass-sched", sizeof base - strlen(base) - 1);
   }
   if (h->world > 1)
     snprintf(h->kname, sizeof h->kname, "%s|x%d:%s", base, h->world, h->exchange == 1 ? "peer-push" : "nccl-bcast");

@@ -39,15 +39,15 @@
 #ifndef NB_MINB6
 #define NB_MINB6 14
 #endif
-// the per-body-mass instantiations keep ptxas' instructions (re-ordered by tools/sass_sched.py): the budgets they were tuned at
+// the per-body-mass instantiations (one more FMUL2 per pair-unit) are regenerated the same way
 #ifndef NB_MINB2M
-#define NB_MINB2M 28
+#define NB_MINB2M NB_MINB2
 #endif
 #ifndef NB_MINB4M
-#define NB_MINB4M 20
+#define NB_MINB4M NB_MINB4
 #endif
 #ifndef NB_MINB6M
-#define NB_MINB6M 14
+#define NB_MINB6M NB_MINB6
 #endif
 // AUTO switch points in bodies per SM (see choose_config)
 #ifndef NB_SW6

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--segs", type=int, default=0, help="NBODY_SEGS override")
     ap.add_argument("--variants", action="store_true", help="load libnbody_b200_variants.so (comparison kernels)")
+    ap.add_argument("--mass", action="store_true", help="per-body masses (uniform in [0.5, 1.5)): times the MASS instantiations")
     a = ap.parse_args()
     if a.cfg:
         os.environ["NBODY_KERNEL_CONFIG"] = a.cfg
@@ -34,6 +35,9 @@ def main():
     lib = nb.load_library(nb.VARIANTS_LIB_PATH) if a.variants or a.kernel in ("packed", "scalar") else None
     sim = nb.DiskGalaxySimulator(nb.SimParam(numParticles=a.n, simIterationsPerFrame=a.iters), n_gpus=a.gpus, lib=lib)
     sim.setKernel(KERNELS[a.kernel])
+    if a.mass:
+        import numpy as np
+        sim.setMass(np.random.default_rng(1).uniform(0.5, 1.5, a.n).astype(np.float32))
     for s in range(a.steps):
         sim.stepSim()
         ms = sim.getLastStepDeviceTime() / a.iters

@@ -2,10 +2,10 @@
 """sass_post.py -- post-link step of the library build (cuda-to-sycl-nbody_b200/Makefile).
 
 For every instantiation of the production kernel force_wseg_kernel<R, MINB, MASS> in the built library:
-  1. tools/sass_gen.py   regenerates the unrolled tile body from scratch (unit-mass instantiations), proving the
-                         new block equivalent to ptxas' block before it is written;
-  2. tools/sass_sched.py re-orders ptxas' own instructions (per-body-mass instantiations, and any kernel step 1
-                         declines), verifying every dependence of the block it writes;
+  1. tools/sass_gen.py   regenerates the unrolled tile body from scratch, proving the new block equivalent to
+                         ptxas' block before it is written;
+  2. tools/sass_sched.py re-orders ptxas' own instructions of any kernel step 1 declines, verifying every
+                         dependence of the block it writes;
   3. otherwise ptxas' code stays as it is.
 Either way the arithmetic instructions are ptxas' encodings of the reference's IEEE operations; results are
 bit-identical (tests/test_parity_gpu.py).  The library records what was done (nbody_kernel_name() reports it).
@@ -25,6 +25,7 @@ import sass_gen as G  # noqa: E402
 import sass_sched as S  # noqa: E402
 
 GEN_MARKER = b"NBODY_SASS_GEN="
+GENM_MARKER = b"NBODY_SASS_GENM="
 
 
 def main():
@@ -41,13 +42,17 @@ def main():
     log = (lambda *x: None) if a.quiet else print
     data = bytearray(open(a.lib, "rb").read())
     names = [n for n in S.function_names(a.lib) if a.kernel in n]
-    n_gen = n_sched = 0
+    n_gen = n_genm = n_sched = 0
     for k in names:
         done = False
+        mass = "Lb1EEE" in k
         if not a.no_gen:
             try:
                 done = G.process(a.lib, k, data, gopt, log)
-                n_gen += 1 if done else 0
+                if done and mass:
+                    n_genm += 1
+                elif done:
+                    n_gen += 1
             except (ValueError, AssertionError, SystemExit) as e:
                 log(f"{k}: not generated ({e})")
         if not done:
@@ -55,12 +60,12 @@ def main():
                 n_sched += 1 if S.process_kernel(a.lib, k, data, sopt, log) else 0
             except (ValueError, AssertionError, SystemExit) as e:
                 log(f"{k}: not scheduled ({e})")
-    for marker, count in ((S.MARKER, n_sched), (GEN_MARKER, n_gen)):
+    for marker, count in ((S.MARKER, n_sched), (GEN_MARKER, n_gen), (GENM_MARKER, n_genm)):
         m = data.find(marker)
         if m >= 0:
             data[m + len(marker):m + len(marker) + 2] = b"%02d" % count
-    print(f"sass_post: {len(names)} kernels: {n_gen} regenerated, {n_sched} re-scheduled, "
-          f"{len(names) - n_gen - n_sched} left as ptxas wrote them ({a.lib})")
+    print(f"sass_post: {len(names)} kernels: {n_gen} + {n_genm} (per-body mass) regenerated, {n_sched} re-scheduled, "
+          f"{len(names) - n_gen - n_genm - n_sched} left as ptxas wrote them ({a.lib})")
     tmp = tempfile.NamedTemporaryFile(dir=os.path.dirname(os.path.abspath(a.lib)), suffix=".so", delete=False)
     tmp.write(bytes(data))
     tmp.close()
