@@ -672,6 +672,7 @@ int nbody_set_kernel(nbody_handle *h, int kernel) {
 extern "C" const volatile char nbody_sass_sched_marker[] = "NBODY_SASS_SCHED=00";
 extern "C" const volatile char nbody_sass_gen_marker[] = "NBODY_SASS_GEN=00";
 extern "C" const volatile char nbody_sass_genm_marker[] = "NBODY_SASS_GENM=00";  // ... of the per-body-mass instantiations
+extern "C" const volatile char nbody_sass_gens_marker[] = "NBODY_SASS_GENS=00";  // ... the scalar small-shard kernel
 
 const char *nbody_kernel_name(nbody_handle *h) {
   if (!h || h->devs.empty()) return "";
@@ -684,6 +685,9 @@ const char *nbody_kernel_name(nbody_handle *h) {
   if (kc.family == nbody::kFamSegmented || kc.family == nbody::kFamUnsegmented) {
     if (kc.mass ? genm : gen) strncat(base, "+sass-gen", sizeof base - strlen(base) - 1);
     else if (sched) strncat(base, "+sass-sched", sizeof base - strlen(base) - 1);
+  } else if (kc.family == nbody::kFamSmall && kc.r == 1 && !kc.mass &&
+             (nbody_sass_gens_marker[16] != '0' || nbody_sass_gens_marker[17] != '0')) {
+    strncat(base, "+sass-gen", sizeof base - strlen(base) - 1);
   }
   if (h->world > 1)
     snprintf(h->kname, sizeof h->kname, "%s|x%d:%s", base, h->world, h->exchange == 1 ? "peer-push" : "nccl-bcast");

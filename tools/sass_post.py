@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """sass_post.py -- post-link step of the library build (cuda-to-sycl-nbody_b200/Makefile).
 
-For every instantiation of the production kernel force_wseg_kernel<R, MINB, MASS> in the built library:
+For every instantiation of the production kernel force_wseg_kernel<R, MINB, MASS> in the built library, and for the
+scalar one-body-per-lane kernel force_wscalar_kernel<1, none, unit mass> AUTO uses for small shards:
   1. tools/sass_gen.py   regenerates the unrolled tile body from scratch, proving the new block equivalent to
                          ptxas' block before it is written;
   2. tools/sass_sched.py re-orders ptxas' own instructions of any kernel step 1 declines, verifying every
@@ -26,6 +27,9 @@ import sass_sched as S  # noqa: E402
 
 GEN_MARKER = b"NBODY_SASS_GEN="
 GENM_MARKER = b"NBODY_SASS_GENM="
+GENS_MARKER = b"NBODY_SASS_GENS="
+# the scalar one-body-per-lane kernel AUTO uses for small shards (R = 1, no self-term predicate, unit mass)
+SCALAR_KERNEL = "force_wscalar_kernelILi1ELi0ELb0"
 
 
 def main():
@@ -41,11 +45,18 @@ def main():
     sopt = argparse.Namespace(pull_window=3, heur=["qgroup"], yield_mode="hold", keep_order=False, no_reuse=False)
     log = (lambda *x: None) if a.quiet else print
     data = bytearray(open(a.lib, "rb").read())
-    names = [n for n in S.function_names(a.lib) if a.kernel in n]
-    n_gen = n_genm = n_sched = 0
+    names = [n for n in S.function_names(a.lib) if a.kernel in n or SCALAR_KERNEL in n]
+    n_gen = n_genm = n_gens = n_sched = 0
     for k in names:
         done = False
         mass = "Lb1EEE" in k
+        if SCALAR_KERNEL in k:  # generated or left alone (sass_sched handles the packed kernels only)
+            if not a.no_gen:
+                try:
+                    n_gens += 1 if G.process(a.lib, k, data, gopt, log) else 0
+                except (ValueError, AssertionError, SystemExit) as e:
+                    log(f"{k}: not generated ({e})")
+            continue
         if not a.no_gen:
             try:
                 done = G.process(a.lib, k, data, gopt, log)
@@ -60,12 +71,12 @@ def main():
                 n_sched += 1 if S.process_kernel(a.lib, k, data, sopt, log) else 0
             except (ValueError, AssertionError, SystemExit) as e:
                 log(f"{k}: not scheduled ({e})")
-    for marker, count in ((S.MARKER, n_sched), (GEN_MARKER, n_gen), (GENM_MARKER, n_genm)):
+    for marker, count in ((S.MARKER, n_sched), (GEN_MARKER, n_gen), (GENM_MARKER, n_genm), (GENS_MARKER, n_gens)):
         m = data.find(marker)
         if m >= 0:
             data[m + len(marker):m + len(marker) + 2] = b"%02d" % count
-    print(f"sass_post: {len(names)} kernels: {n_gen} + {n_genm} (per-body mass) regenerated, {n_sched} re-scheduled, "
-          f"{len(names) - n_gen - n_genm - n_sched} left as ptxas wrote them ({a.lib})")
+    print(f"sass_post: {len(names)} kernels: {n_gen} + {n_genm} (per-body mass) + {n_gens} (scalar small-shard) regenerated, "
+          f"{n_sched} re-scheduled, {len(names) - n_gen - n_genm - n_gens - n_sched} left as ptxas wrote them ({a.lib})")
     tmp = tempfile.NamedTemporaryFile(dir=os.path.dirname(os.path.abspath(a.lib)), suffix=".so", delete=False)
     tmp.write(bytes(data))
     tmp.close()
