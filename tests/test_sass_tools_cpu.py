@@ -40,11 +40,15 @@ def test_library_records_the_post_link_step():
     s = raw.find(b"NBODY_SASS_SCHED=")
     assert g >= 0 and s >= 0
     gm = raw.find(b"NBODY_SASS_GENM=")
+    gs = raw.find(b"NBODY_SASS_GENS=")
     n_gen = int(raw[g + 15:g + 17])
     n_genm = int(raw[gm + 16:gm + 18])
+    n_gens = int(raw[gs + 16:gs + 18])
     n_sched = int(raw[s + 17:s + 19])
-    # every production instantiation (R = 2, 4, 6, unit mass and per-body mass) carries a generated tile body
-    assert (n_gen, n_genm, n_sched) == (3, 3, 0), (n_gen, n_genm, n_sched)
+    # every production instantiation (R = 2, 4, 6, unit mass and per-body mass) and the scalar small-shard kernel
+    # carry a generated tile body
+    assert (n_gen, n_genm, n_sched) == (3, 3, 0), (n_gen, n_genm, n_gens, n_sched)
+    assert n_gens in (0, 1)  # the scalar kernel's generated body is a build option (GEN_SCALAR)
 
 
 def test_generator_proof_accepts_its_output_and_rejects_corruption(tmp_path):
@@ -116,3 +120,23 @@ def test_every_period_template_generates_a_proven_block(tmp_path, template):
     blk = _patched_block(tmp_path, m, ops, kernel)
     assert G.equivalent(m.block, blk, [r for a in m.acc_out_regs for r in (a, a + 1)]) == []
     assert S.verify(blk, m.fixed_lat) == 0
+
+
+def test_scalar_small_shard_kernel_generates_a_proven_block(tmp_path):
+    """the scalar one-body-per-lane kernel (32-bit registers, every j-body accumulates into the SAME three registers,
+    so the proof also pins the ascending-j order of the accumulate triplets)"""
+    import sass_gen as G
+    import sass_sched as S
+    kernel = [n for n in S.function_names(LIB) if "force_wscalar_kernelILi1ELi0ELb0" in n][0]
+    m = G.Model(LIB, kernel)
+    assert m.scalar and m.W == 1 and m.R2 == 1 and m.n_j == 32 and len(m.live_out) == 3
+    ap = argparse.ArgumentParser()
+    G.add_options(ap)
+    ops = G.generate(m, ap.parse_args([]))
+    blk = G.parse_scalar_ops(_patched_block(tmp_path, m, ops, kernel))
+    assert G.equivalent(m.block, blk, m.live_out) == []
+    assert S.verify(blk, m.fixed_lat) == 0
+    # a template that accumulates the later unit of a period first breaks the ascending-j order: must be rejected
+    bad = G.generate(m, ap.parse_args(["--scalar-template", "Ay* Ax* Az* c1* c4*:1 c2* c5*:1 c3* c6*:1 T1:2 T0:2"]))
+    blk = G.parse_scalar_ops(_patched_block(tmp_path, m, bad, kernel))
+    assert G.equivalent(m.block, blk, m.live_out) != []

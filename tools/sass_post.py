@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--kernel", default="force_wseg_kernelILi")
     ap.add_argument("--no-gen", action="store_true", help="only re-order ptxas' code (tools/sass_sched.py)")
     ap.add_argument("--quiet", action="store_true")
+    ap.add_argument("--gen-scalar", action="store_true",
+                    help="also regenerate the scalar small-shard kernel (off until validated on hardware: GEN_SCALAR=1 in the Makefile)")
     a, rest = ap.parse_known_args()
     gp = argparse.ArgumentParser()
     G.add_options(gp)
@@ -51,7 +53,7 @@ def main():
         done = False
         mass = "Lb1EEE" in k
         if SCALAR_KERNEL in k:  # generated or left alone (sass_sched handles the packed kernels only)
-            if not a.no_gen:
+            if not a.no_gen and a.gen_scalar:
                 try:
                     n_gens += 1 if G.process(a.lib, k, data, gopt, log) else 0
                 except (ValueError, AssertionError, SystemExit) as e:
