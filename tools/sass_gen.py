@@ -326,6 +326,8 @@ TEMPLATES = {
     "scalar": "Ay* Ax* Az* c1* c4*:1 c2* c5*:1 c3* c6*:1 T0:2 T1:2",
     "scalar_mid": "Ay* Ax* Az* c1* c4*:1 c2* c5*:1 T0:2 c3* c6*:1 T1:2",
     "scalar3": "Ay* Ax* Az* c1* c4*:1 c2* c5*:1 c3* c6*:1 T0:3 T1:3",
+    "scalar_mid3": "Ay* Ax* Az* c1* c4*:1 c2* c5*:1 T0:3 c3* c6*:1 T1:3",
+    "scalar_apart": "Ay* Ax* Az* T1:3 c1* c4*:1 c2* c5*:1 c3* c6*:1 T0:2",
 }
 
 
@@ -681,6 +683,12 @@ def process(lib, kernel, data, opt, log):
     m = Model(lib, kernel)
     log(f"{m.name}: tile body {m.n} instructions, {m.n_j} j-bodies x {m.R2} {'scalar ' if m.scalar else 'pair-'}units; "
         f"{len(m.free)} free registers, scoreboards LDS {m.lds_bar} MUFU {m.mufu_bars}, latencies {m.fixed_lat}")
+    if m.scalar:  # the scalar small-shard kernel has its own knobs (one warp per sub-partition: latencies are not hidden)
+        opt = argparse.Namespace(**vars(opt))
+        for k in ("quads", "lds_ahead", "lds_early", "mufu_gap", "extra_buf"):
+            v = getattr(opt, "scalar_" + k, None)
+            if v is not None:
+                setattr(opt, k, v)
     ops = None
     for nq in range(opt.quads, 10):  # per-body masses keep a tile word alive until the accumulates: more LDS buffers
         try:
@@ -729,6 +737,11 @@ def add_options(ap):
     ap.add_argument("--lds-ahead", type=int, default=1, help="periods between an LDS and the first use of its tile word")
     ap.add_argument("--lds-early", action="store_true", help="issue the period's LDS in front of its differences instead of behind them")
     ap.add_argument("--scalar-template", default="scalar", help="template of the scalar one-body-per-lane kernel")
+    ap.add_argument("--scalar-quads", type=int, default=None, help="--quads of the scalar kernel (default: --quads)")
+    ap.add_argument("--scalar-lds-ahead", type=int, default=None)
+    ap.add_argument("--scalar-lds-early", action="store_true", default=None)
+    ap.add_argument("--scalar-mufu-gap", type=int, default=None)
+    ap.add_argument("--scalar-extra-buf", type=int, default=None)
     ap.add_argument("--mufu-gap", type=int, default=10, help="minimum cycles between two MUFUs of the warp")
     ap.add_argument("--no-mufu-between", dest="mufu_between", action="store_false",
                     help="no MUFU in the shadow of the last accumulate of a triplet")
