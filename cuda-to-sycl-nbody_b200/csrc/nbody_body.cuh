@@ -360,4 +360,122 @@ __device__ __forceinline__ void warp_sweep_scalar(const StepArgs &a, const uint3
   }
 }
 
+// ---- accumulator relay (small shards) --------------------------------------------------------------
+// With fewer i-bodies than the machine has lanes, one warp per 32 bodies leaves every SM sub-partition with at
+// most one warp, and a single warp issues only ~0.6 instructions per cycle (profiles/r02_ncu_wscalar_*).  More
+// warps cannot come from the bodies -- but they can come from the j-loop WITHOUT touching the summation order:
+// W warps of one CTA serve the SAME 32 i-bodies and take the j-tiles round-robin.  For its tile a warp first
+// computes everything that does not depend on the running sums -- the differences r and the weights
+// w = rsqrt((r^2+eps)^3), 10 of the 13 operations -- into registers; then it takes the accumulators from the warp
+// that handled the previous tile (through shared memory), runs the 3 x TJ accumulate FMAs in ascending j, and
+// passes them on.  Every lane still owns one FP32 chain per component over ascending j: bit-identical.
+// The serial part is the FMA chain alone (4 cycles per j) instead of the whole 13-op body.
+// The hand-off uses one shared-memory mbarrier per warp ("your turn"): the warp that finishes tile t stores its
+// lanes' sums and arrives (release) on the barrier of the warp that holds tile t + 1; that warp sleeps in
+// mbarrier.try_wait (acquire) instead of spinning -- a spin loop would take issue slots from the warps of other
+// CTAs that share the sub-partition (measured: profiles/r02_relay.txt).  Every lane arrives, so each lane's own
+// store is ordered before the wake-up of the same lane of the next warp.
+__device__ __forceinline__ void mbar_init(u64 *bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned int)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64 *bar) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n}" ::"r"((unsigned int)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, unsigned int parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n"
+      "RELAY_WAIT:\n"
+      " mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra RELAY_DONE;\n"
+      " bra RELAY_WAIT;\n"
+      "RELAY_DONE:\n}" ::"r"((unsigned int)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+template <int W, int TJ, bool MASS>
+__device__ __forceinline__ void cta_relay_scalar(const StepArgs &a, float4 (*tile)[TJ], float4 *tok, u64 *bar) {
+  static_assert(TJ == 16 || TJ == 32, "one coalesced load per tile");
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t li = blockIdx.x * 32u + lane;
+  const uint32_t lc = li < a.i_count ? li : a.i_count - 1;
+  const float4 own = a.pos[a.i_begin + lc];
+  const float nx = -own.x, ny = -own.y, nz = -own.z;
+  const float eps = a.eps;
+  const uint32_t nj = a.j_end - a.j_begin;
+  const uint32_t ntiles = (nj + TJ - 1) / TJ;
+  float ax = 0.0f, ay = 0.0f, az = 0.0f;
+  if (w == 0) {  // warp 0 takes tile 0 and with it the incoming sums
+    if (!(a.flags & kFirstChunk)) {
+      const float4 c = __ldcg(&a.acc[lc]);
+      ax = c.x;
+      ay = c.y;
+      az = c.z;
+    }
+    if (ntiles == 0) {
+      if (li < a.i_count) finish_body(a, a.flags, li, ax, ay, az, own);
+      return;
+    }
+  }
+  if (ntiles == 0) return;
+  if (threadIdx.x < W) mbar_init(&bar[threadIdx.x], 32u);  // bar[w]: the 32 lanes holding the previous tile have arrived
+  __syncthreads();
+  unsigned int turns = 0;  // completed waits of this warp = phase parity of its barrier
+  const uint32_t last = a.j_end - 1;
+  const int jl = lane & (TJ - 1);
+  float4 nxt = a.pos[min(a.j_begin + (uint32_t)w * TJ + jl, last)];
+  for (uint32_t t = w; t < ntiles; t += W) {
+    __syncwarp();  // every lane is done reading the previous tile
+    if (TJ == 32 || lane < TJ) tile[w][jl] = nxt;
+    nxt = a.pos[min(a.j_begin + (t + W) * TJ + jl, last)];  // always fetched (clamped): branch-free bookkeeping
+    __syncwarp();
+    float rx[TJ], ry[TJ], rz[TJ], wt[TJ];
+#pragma unroll
+    for (int j = 0; j < TJ; j++) {  // a ragged last tile computes its unused entries from the clamped re-read
+      const float4 q = tile[w][j];
+      rx[j] = fadd(q.x, nx);
+      ry[j] = fadd(q.y, ny);
+      rz[j] = fadd(q.z, nz);
+      float s = fmul(ry[j], ry[j]);
+      s = ffma(rx[j], rx[j], s);
+      s = ffma(rz[j], rz[j], s);
+      const float d = fadd(s, eps);
+      float c = fmul(d, d);
+      c = fmul(d, c);
+      wt[j] = frsq(c);
+      if (MASS) wt[j] = fmul(wt[j], q.w);
+    }
+    if (t > 0) {  // the sums arrive from the warp that handled tile t - 1
+      mbar_wait(&bar[w], turns & 1u);
+      turns++;
+      const float4 k = tok[lane];
+      ax = k.x;
+      ay = k.y;
+      az = k.z;
+    }
+    const uint32_t cnt = min((uint32_t)TJ, nj - t * TJ);
+    if (cnt == TJ) {
+#pragma unroll
+      for (int j = 0; j < TJ; j++) {
+        ax = ffma(rx[j], wt[j], ax);
+        ay = ffma(ry[j], wt[j], ay);
+        az = ffma(rz[j], wt[j], az);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < TJ; j++) {
+        if (j < cnt) {
+          ax = ffma(rx[j], wt[j], ax);
+          ay = ffma(ry[j], wt[j], ay);
+          az = ffma(rz[j], wt[j], az);
+        }
+      }
+    }
+    if (t + 1 < ntiles) {  // hand the sums to the warp that holds tile t + 1
+      tok[lane] = make_float4(ax, ay, az, 0.0f);
+      mbar_arrive(&bar[(w + 1) % W]);
+    } else if (li < a.i_count) {
+      finish_body(a, a.flags, li, ax, ay, az, own);
+    }
+  }
+}
+
 }  // namespace nbody

@@ -696,6 +696,14 @@ const char *nbody_kernel_name(nbody_handle *h) {
   return h->kname;
 }
 
+int nbody_describe_auto(const nbody_params *p, uint64_t shard_bodies, int sms, int has_mass, char *buf, size_t len) {
+  if (!p || !buf || len == 0 || sms < 1 || shard_bodies == 0 || shard_bodies > 0xffffffffull)
+    return fail(NBODY_E_INVALID, "nbody_describe_auto: bad argument");
+  const nbody::KernelConfig kc = nbody::choose_config(0 /*AUTO*/, p->calc_method, p->dist_eps, (uint32_t)shard_bodies, sms, has_mass != 0);
+  nbody::config_name(kc, buf, len);
+  return 0;
+}
+
 int nbody_set_state(nbody_handle *h, const float *x, const float *y, const float *z, const float *vx,
                     const float *vy, const float *vz) {
   if (!h || !x || !y || !z || !vx || !vy || !vz) return fail(NBODY_E_INVALID, "null argument");

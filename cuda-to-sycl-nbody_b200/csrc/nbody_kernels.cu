@@ -56,6 +56,13 @@
 #ifndef NB_SW4
 #define NB_SW4 1650u
 #endif
+// accumulator relay (smallest shards): up to 3 / 4 resident CTAs of 32 bodies per SM
+#ifndef NB_RELAY32
+#define NB_RELAY32 96u
+#endif
+#ifndef NB_RELAY16
+#define NB_RELAY16 128u
+#endif
 
 namespace nbody {
 
@@ -111,6 +118,16 @@ __global__ void __launch_bounds__(32) force_wscalar_kernel(const StepArgs a) {
   const uint32_t warp_i = blockIdx.x * (uint32_t)(32 * R);
   if (warp_i >= a.i_count) return;
   warp_sweep_scalar<R, SELF, MASS>(a, a.j_begin, a.j_end, a.flags, warp_i, s_tile, lane);
+}
+
+// accumulator relay: W warps per CTA serve the same 32 i-bodies, j-tiles of TJ bodies round-robin (cta_relay_scalar)
+template <int W, int TJ, int MINB, bool MASS>
+__global__ void __launch_bounds__(32 * W, MINB) force_wrelay_kernel(const StepArgs a) {
+  __shared__ __align__(16) float4 s_tile[W][TJ];
+  __shared__ __align__(16) float4 s_tok[32];
+  __shared__ __align__(8) u64 s_bar[W];
+  if (blockIdx.x * 32u >= a.i_count) return;
+  cta_relay_scalar<W, TJ, MASS>(a, s_tile, s_tok, s_bar);
 }
 
 // ---- layout helpers -------------------------------------------------------------------------
@@ -202,7 +219,15 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
     r = 6;
     if ((uint64_t)i_count < (uint64_t)sms * NB_SW6) r = 4;
     if ((uint64_t)i_count < (uint64_t)sms * NB_SW4) r = 2;
-    if ((uint64_t)i_count < (uint64_t)sms * 768u) {
+    if ((uint64_t)i_count <= (uint64_t)sms * NB_RELAY16) {
+      // smallest shards (at most 4 groups of 32 bodies per SM): even the scalar kernel leaves each sub-partition
+      // with one warp at 0.6 instructions per cycle.  The accumulator relay turns one group into 4 warps without
+      // changing the summation order (cta_relay_scalar): measured 1.25x at N = 12 800, 1.6-1.8x at 2K-6.4K bodies,
+      // 1.13x at 18 944 (profiles/r02_relay.txt).  32-body tiles need 164 registers = 3 CTAs per SM, 16-body tiles 108 = 4.
+      family = kFamRelay;
+      block = 128;
+      r = (uint64_t)i_count <= (uint64_t)sms * NB_RELAY32 ? 32 : 16;
+    } else if ((uint64_t)i_count < (uint64_t)sms * 768u) {
       static const double eff[3][4] = {{0.376, 0.47, 0.53, 0.57},   // scalar, 1 / 2 / 3 / >= 4 warps per sub-partition
                                        {0.58, 0.66, 0.72, 0.74},    // R = 2
                                        {0.68, 0.74, 0.755, 0.763}}; // R = 4
@@ -238,7 +263,7 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
     if (got >= 2 && er > 0 && eb > 0) {
       r = er;
       block = eb;
-      if (got == 3 && ef >= 1 && ef <= 6) family = ef;
+      if (got == 3 && ef >= 1 && ef <= 7) family = ef;
     }
   }
   c = {family, r, block, kSelfNone, sms, has_mass ? 1 : 0};
@@ -246,9 +271,9 @@ KernelConfig choose_config(int requested_kernel, int calc_method, float eps, uin
 }
 
 const char *config_name(const KernelConfig &c, char *buf, size_t len) {
-  static const char *fam[] = {"generic_scalar", "cta_packed_f32x2", "cta_scalar", "wstream_f32x2", "wseg_f32x2", "wseg_tma_f32x2", "wsmall_scalar"};
+  static const char *fam[] = {"generic_scalar", "cta_packed_f32x2", "cta_scalar", "wstream_f32x2", "wseg_f32x2", "wseg_tma_f32x2", "wsmall_scalar", "wrelay_scalar"};
   static const char *self[] = {"nopred", "branch", "predicated", "predicated_fixed"};
-  snprintf(buf, len, "%s_r%d_b%d_%s%s", fam[c.family >= 0 && c.family <= 6 ? c.family : 0], c.r, c.block,
+  snprintf(buf, len, "%s_r%d_b%d_%s%s", fam[c.family >= 0 && c.family <= 7 ? c.family : 0], c.r, c.block,
            self[c.self_mode >= 0 && c.self_mode <= 3 ? c.self_mode : 0], c.mass ? "_mass" : "");
   return buf;
 }
@@ -336,6 +361,16 @@ static cudaError_t launch_wscalar(const StepArgs &a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+template <int W, int TJ, int MINB>
+static cudaError_t launch_wrelay(const StepArgs &a, bool mass, cudaStream_t s) {
+  const uint32_t ctas = (a.i_count + 31u) / 32u;
+  if (mass)
+    force_wrelay_kernel<W, TJ, MINB, true><<<ctas, 32 * W, 0, s>>>(a);
+  else
+    force_wrelay_kernel<W, TJ, MINB, false><<<ctas, 32 * W, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_step(const KernelConfig &c, const StepArgs &a, cudaStream_t s) {
   if (a.i_count == 0) return cudaSuccess;
   const bool m = c.mass != 0;
@@ -349,6 +384,14 @@ cudaError_t launch_step(const KernelConfig &c, const StepArgs &a, cudaStream_t s
   if (c.family == kFamSmall) {
     if (c.r == 1) return m ? launch_wscalar<1, kSelfNone, true>(a, s) : launch_wscalar<1, kSelfNone, false>(a, s);
     if (c.r == 2) return m ? launch_wscalar<2, kSelfNone, true>(a, s) : launch_wscalar<2, kSelfNone, false>(a, s);
+    return cudaErrorInvalidConfiguration;
+  }
+  if (c.family == kFamRelay) {  // (warps per CTA, j-bodies per tile): register budget = resident CTAs promised to ptxas
+    if (c.block == 128 && c.r == 16) return launch_wrelay<4, 16, 4>(a, m, s);
+    if (c.block == 128 && c.r == 32) return launch_wrelay<4, 32, 3>(a, m, s);
+    if (c.block == 64 && c.r == 16) return launch_wrelay<2, 16, 8>(a, m, s);
+    if (c.block == 64 && c.r == 32) return launch_wrelay<2, 32, 6>(a, m, s);
+    if (c.block == 256 && c.r == 16) return launch_wrelay<8, 16, 2>(a, m, s);
     return cudaErrorInvalidConfiguration;
   }
   if (c.family == kFamSegmented || c.family == kFamUnsegmented) {

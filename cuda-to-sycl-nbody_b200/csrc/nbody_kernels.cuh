@@ -63,6 +63,7 @@ enum Family : int {
   kFamSegmented = 4,   // production: warp-streaming packed f32x2 with j-segmented hand-off
   kFamTma = 5,         // comparison: TMA-staged production kernel       (VARIANTS build only)
   kFamSmall = 6,       // small shards: scalar, one body per lane, no predicate
+  kFamRelay = 7,       // smallest shards: block/32 warps relay the sums of the same 32 bodies over j-tiles of r bodies
 };
 
 struct KernelConfig {

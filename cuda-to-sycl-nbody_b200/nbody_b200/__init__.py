@@ -32,7 +32,7 @@ KERNEL_AUTO, KERNEL_GENERIC, KERNEL_PACKED, KERNEL_SCALAR = 0, 1, 2, 3
 ABI_SYMBOLS = [
     "nbody_abi_version", "nbody_last_error", "nbody_device_count", "nbody_default_params",
     "nbody_generate_disk_galaxy", "nbody_plan_shard", "nbody_create", "nbody_create_rank", "nbody_nccl_unique_id",
-    "nbody_destroy", "nbody_set_kernel", "nbody_kernel_name", "nbody_set_state", "nbody_set_mass",
+    "nbody_destroy", "nbody_set_kernel", "nbody_kernel_name", "nbody_describe_auto", "nbody_set_state", "nbody_set_mass",
     "nbody_step", "nbody_last_step_ms", "nbody_last_step_device_ms", "nbody_launch_count",
     "nbody_read_pos", "nbody_read_vel", "nbody_read_pos_f4", "nbody_read_vel_f4",
     "nbody_read_state", "nbody_local_range", "nbody_read_local", "nbody_host_register", "nbody_host_unregister",
@@ -107,6 +107,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.nbody_nccl_unique_id.argtypes = [ctypes.c_void_p]
     lib.nbody_destroy.argtypes = [H]
     lib.nbody_set_kernel.argtypes = [H, ctypes.c_int]
+    lib.nbody_describe_auto.argtypes = [ctypes.POINTER(Params), ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_char_p, ctypes.c_size_t]
     lib.nbody_kernel_name.argtypes = [H]
     lib.nbody_kernel_name.restype = ctypes.c_char_p
     lib.nbody_set_state.argtypes = [H] + [_fp] * 6
@@ -172,6 +174,15 @@ def plan_shard(n: int, world: int, rank: int) -> tuple[int, int]:
     b, c = ctypes.c_uint64(), ctypes.c_uint64()
     _check(lib, lib.nbody_plan_shard(n, world, rank, ctypes.byref(b), ctypes.byref(c)), "nbody_plan_shard")
     return int(b.value), int(c.value)
+
+
+def describe_auto(n: int, sms: int = 148, has_mass: bool = False, params: "SimParam | None" = None, lib=None) -> str:
+    """the kernel configuration AUTO picks for a shard of n bodies on a device with `sms` SMs (host-only)"""
+    lib = lib or load_library()
+    buf = ctypes.create_string_buffer(96)
+    c = (params or SimParam()).to_c()
+    _check(lib, lib.nbody_describe_auto(ctypes.byref(c), n, sms, int(has_mass), buf, len(buf)), "nbody_describe_auto")
+    return buf.value.decode()
 
 
 def nccl_unique_id() -> bytes:

@@ -126,6 +126,13 @@ int nbody_destroy(nbody_handle *h);
 int nbody_set_kernel(nbody_handle *h, int kernel);
 /* human-readable description of the kernel configuration the next step will use */
 const char *nbody_kernel_name(nbody_handle *h);
+/*
+ * Host-only: the configuration AUTO picks for a shard of `shard_bodies` i-bodies on a device with `sms` SMs
+ * (`has_mass`: per-body masses set).  Same naming as nbody_kernel_name() without the post-link suffix.  Needs no
+ * GPU: lets a caller (and the CPU test-suite) see the kernel switch points.  The reference has one kernel and no
+ * such choice (src/simulator.cu:60-66 launches particle_interaction<> with gwSize threads whatever N is).
+ */
+int nbody_describe_auto(const nbody_params *p, uint64_t shard_bodies, int sms, int has_mass, char *buf, size_t len);
 
 /*
  * Replaces DiskGalaxySimulator::sendToDevice (src/simulator.cu:79-103) for caller-provided

@@ -150,3 +150,29 @@ def test_shard_plan_properties_hypothesis(nb):
         assert pos == n
 
     check()
+
+
+def test_auto_switch_points(nb):
+    """AUTO's kernel choice per shard size on a 148-SM device (host-only nbody_describe_auto): accumulator relay for the
+    smallest shards (<= 3 / 4 groups of 32 bodies per SM), the quantisation cost model up to 768 bodies per SM, then
+    R = 2 / 4 / 6 of the production kernel; PREDICATED and eps = 0 always take the generic scalar kernel."""
+    d = lambda n, **k: nb.describe_auto(n, 148, **k)
+    assert d(1) == d(2048) == d(12800) == d(148 * 96) == "wrelay_scalar_r32_b128_nopred"
+    assert d(148 * 96 + 1) == d(18944) == "wrelay_scalar_r16_b128_nopred"
+    assert d(12800, has_mass=True) == "wrelay_scalar_r32_b128_nopred_mass"
+    for n in (18945, 25600, 40000, 57720, 64000, 100000):
+        assert d(n) in ("wsmall_scalar_r1_b32_nopred", "wseg_f32x2_r2_b32_nopred", "wseg_f32x2_r4_b32_nopred"), (n, d(n))
+    assert d(131072) == "wseg_f32x2_r2_b32_nopred"
+    assert d(262144) == "wseg_f32x2_r4_b32_nopred"
+    assert d(1048576) == d(4194304 // 8) == "wseg_f32x2_r6_b32_nopred"
+    assert d(1048576, has_mass=True) == "wseg_f32x2_r6_b32_nopred_mass"
+    # a shard of an 8-GPU run is chosen by ITS size, not by N
+    assert d(102400 // 8) == "wrelay_scalar_r32_b128_nopred"
+    # the faithful paths never leave the generic kernel
+    assert d(12800, params=nb.SimParam(calcMethod=nb.CALC_PREDICATED)) == "generic_scalar_r1_b32_predicated"
+    assert d(12800, params=nb.SimParam(distEps=0.0)) == "generic_scalar_r1_b32_branch"
+    # other machine sizes scale the switch points with the SM count
+    assert nb.describe_auto(132 * 96, 132) == "wrelay_scalar_r32_b128_nopred"
+    assert nb.describe_auto(132 * 96 + 1, 132) == "wrelay_scalar_r16_b128_nopred"
+    with pytest.raises(nb.NBodyError):
+        nb.describe_auto(0, 148)

@@ -649,3 +649,54 @@ def test_read_state_read_local_and_registered_host_memory(nb):
     for a in one:
         assert lib.nbody_host_unregister(a.ctypes.data_as(ctypes.c_void_p)) == 0
     sim.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# accumulator relay (AUTO's choice for the smallest shards): W warps of a CTA serve the same 32 bodies
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,cfg", [(2048, None), (12800, None), (14208, None), (14209, None), (18944, None),
+                                   (4099, "16,64,7"), (4099, "32,64,7"), (4099, "16,256,7"), (20011, "32,128,7"),
+                                   (20011, "16,128,7"), (33, "32,128,7"), (17, "16,64,7")])
+def test_relay_kernel_forces_and_steps_vs_reference(nb, ref, n, cfg, monkeypatch):
+    """every shape of force_wrelay_kernel (warps per CTA x bodies per tile) at ragged sizes: forces and the state after
+    2 x 5 iterations are bit-equal to the unmodified reference kernel's (the sums travel between warps through shared
+    memory, so the integrate epilogue runs in whichever warp took the last tile)"""
+    if cfg:
+        monkeypatch.setenv("NBODY_KERNEL_CONFIG", cfg)
+    fx, fy, fz, _ = ref.reference_forces(n)
+    sim = _mk(nb, n, simIterationsPerFrame=5)
+    name = sim.kernelName()
+    assert "wrelay_scalar" in name, name
+    if cfg:
+        r, b, _f = cfg.split(",")
+        assert f"_r{r}_b{b}_" in name, name
+    _assert_bits(sim.computeAccel(), [fx, fy, fz], f"forces N={n} ({name})")
+    rs = ref.RefSimulator(n, iters=5)
+    for _ in range(2):
+        rs.step()
+        sim.stepSim()
+    _assert_bits(_state(sim), rs.state(), f"state after 10 iterations N={n} ({name})")
+    rs.close()
+    sim.close()
+
+
+@pytest.mark.parametrize("n", [1000, 12800, 18944])
+def test_relay_kernel_with_masses_equals_scalar_kernel(nb, n, monkeypatch):
+    """per-body masses through the relay kernel: bit-equal to the one-body-per-lane scalar kernel (which
+    test_masses_exact_properties_and_oracle pins), forces and a 6-iteration state"""
+    m = np.random.default_rng(n).uniform(0.25, 4.0, n).astype(np.float32)
+    out = {}
+    for label, cfg in (("relay", None), ("scalar", "1,32,6")):
+        if cfg:
+            monkeypatch.setenv("NBODY_KERNEL_CONFIG", cfg)
+        sim = _mk(nb, n, simIterationsPerFrame=3)
+        sim.setMass(m)
+        name = sim.kernelName()
+        assert ("wrelay_scalar" if label == "relay" else "wsmall_scalar_r1") in name and "mass" in name, name
+        f = sim.computeAccel()
+        sim.stepSim()
+        sim.stepSim()
+        out[label] = (f, _state(sim))
+        sim.close()
+    _assert_bits(out["relay"][0], out["scalar"][0], f"forces with masses N={n}")
+    _assert_bits(out["relay"][1], out["scalar"][1], f"state with masses N={n}")
