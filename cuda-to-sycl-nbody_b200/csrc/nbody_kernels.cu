@@ -12,6 +12,11 @@
 //     one warp per CTA, scalar ops, one (or two) bodies per lane: small shards (lanes, not issue
 //     slots, are scarce there) and the generic/faithful path with the reference's self-term variants
 //     (BRANCH predicate for any eps, PREDICATED as shipped, PREDICATED as the README intends);
+//   * force_wrelay_kernel<W, TJ, MINB, MASS>  (AUTO below 128 bodies per SM)
+//     W warps per CTA serve the SAME 32 i-bodies and take the j-tiles round-robin: a warp computes the differences
+//     and weights of its tile into registers (10 of the 13 operations, no dependence on the running sums), then
+//     receives the sums from the warp of the previous tile (shared memory + mbarrier), runs the accumulate FMAs in
+//     ascending j and passes them on -- more warps out of the same bodies without touching the summation order;
 //   * no warp shuffles, no atomics, no j-split reduction in the accumulate: a per-thread FMA chain.
 // Comparison kernels (CTA-tiled, TMA-staged) live in nbody_variants.cu and are only built with
 // `make VARIANTS=1`.  Measurements behind every choice: profiles/, DESIGN.md section 5.
