@@ -394,9 +394,11 @@ cudaError_t launch_step(const KernelConfig &c, const StepArgs &a, cudaStream_t s
   if (c.family == kFamRelay) {  // (warps per CTA, j-bodies per tile): register budget = resident CTAs promised to ptxas
     if (c.block == 128 && c.r == 16) return launch_wrelay<4, 16, 4>(a, m, s);
     if (c.block == 128 && c.r == 32) return launch_wrelay<4, 32, 3>(a, m, s);
+#ifdef NBODY_VARIANTS  // shapes AUTO never picks (measured slower, profiles/r02_relay.txt): comparison build only
     if (c.block == 64 && c.r == 16) return launch_wrelay<2, 16, 8>(a, m, s);
     if (c.block == 64 && c.r == 32) return launch_wrelay<2, 32, 6>(a, m, s);
     if (c.block == 256 && c.r == 16) return launch_wrelay<8, 16, 2>(a, m, s);
+#endif
     return cudaErrorInvalidConfiguration;
   }
   if (c.family == kFamSegmented || c.family == kFamUnsegmented) {
