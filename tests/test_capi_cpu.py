@@ -176,3 +176,63 @@ def test_auto_switch_points(nb):
     assert nb.describe_auto(132 * 96 + 1, 132) == "wrelay_scalar_r16_b128_nopred"
     with pytest.raises(nb.NBodyError):
         nb.describe_auto(0, 148)
+
+
+def test_auto_choice_properties_hypothesis(nb):
+    """AUTO over arbitrary shard sizes and SM counts: always one of the shipped kernels; the relay exactly up to 128
+    bodies per SM; above 768 bodies per SM the register-blocking factor never shrinks as the shard grows"""
+    from hypothesis import given, settings, strategies as st
+
+    names = {"wrelay_scalar_r32_b128_nopred": 0, "wrelay_scalar_r16_b128_nopred": 0, "wsmall_scalar_r1_b32_nopred": 1,
+             "wseg_f32x2_r2_b32_nopred": 2, "wseg_f32x2_r4_b32_nopred": 4, "wseg_f32x2_r6_b32_nopred": 6}
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(1, 1 << 24), st.integers(1, 1 << 24), st.integers(64, 192))
+    def prop(n1, n2, sms):
+        a, b = sorted((n1, n2))
+        ka, kb = nb.describe_auto(a, sms), nb.describe_auto(b, sms)
+        assert ka in names and kb in names
+        assert ("wrelay" in ka) == (a <= 128 * sms)
+        assert ("_r32_b128" in ka) == (a <= 96 * sms)
+        if a >= 768 * sms:
+            assert names[ka] >= 2 and names[kb] >= names[ka]
+        assert nb.describe_auto(a, sms, has_mass=True) == ka + "_mass"
+
+    prop()
+
+
+def test_relay_turn_protocol_model():
+    """model of the accumulator relay's hand-off (csrc/nbody_body.cuh, cta_relay_scalar): warp w takes tiles w, w + W, ...;
+    before tile t > 0 it waits on ITS barrier with parity (number of its earlier waits) & 1; after tile t it arrives on
+    the barrier of warp (w + 1) % W unless t is the last tile.  Under any interleaving of the warps the tiles are
+    accumulated in ascending order, every wait is eventually satisfied, and a warp never finds more than one completed
+    phase it has not waited for (the parity bit would alias)."""
+    import random
+
+    for W in (2, 4, 8):
+        for ntiles in list(range(0, 20)) + [37, 64, 101]:
+            rng = random.Random(W * 1000 + ntiles)
+            phase = [0] * W            # completed phases per barrier
+            nxt = [w for w in range(W)]  # next tile of each warp
+            waits = [0] * W
+            order = []
+            stuck = 0
+            while any(t < ntiles for t in nxt):
+                w = rng.randrange(W)
+                t = nxt[w]
+                if t >= ntiles:
+                    continue
+                if t > 0:
+                    if phase[w] <= waits[w]:      # try_wait(parity = waits & 1) not yet satisfied
+                        stuck += 1
+                        assert stuck < 100000, "deadlock"
+                        continue
+                    assert phase[w] == waits[w] + 1, "a phase was skipped"
+                    waits[w] += 1
+                stuck = 0
+                order.append(t)
+                if t + 1 < ntiles:
+                    d = (w + 1) % W
+                    phase[d] += 1                 # all 32 lanes arrive: the phase completes
+                nxt[w] = t + W
+            assert order == list(range(ntiles))
